@@ -1,0 +1,163 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+TEST INFRASTRUCTURE.  Run in the build container only (the reference tree does not
+travel to the GPU box):   python -m oracle.gen_golden
+Everything is seeded; fixtures are small (reduced ngf/ndf and image sizes) so the
+committed files stay well under a few MB.  Fixture layout (np.savez_compressed):
+  sd.<key>      reference state_dict entries
+  in.<name>     inputs fed to the reference module
+  out.<name>    outputs / losses produced by the reference
+  grad.<key>    parameter gradients of `loss = sum(out * proj)` (proj stored as in.proj)
+"""
+import contextlib
+import io
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_loader as R  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def seed(s):
+    random.seed(s)
+    np.random.seed(s)
+    torch.manual_seed(s)
+
+
+def pack(prefix, d):
+    return {"%s.%s" % (prefix, k): (v.detach().cpu().numpy().copy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def module_fixture(name, net, inputs, call, extra=None):
+    """forward + backward of sum(out*proj) through a reference module."""
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    for t in inputs.values():
+        if t.is_floating_point():
+            t.requires_grad_(True)
+    out = call(net, **inputs)
+    proj = torch.randn_like(out)
+    (out * proj).sum().backward()
+    blob = {}
+    blob.update(pack("sd", sd0))
+    blob.update(pack("in", {k: v for k, v in inputs.items()}))
+    blob["in.proj"] = proj.numpy()
+    blob["out.y"] = out.detach().numpy()
+    blob.update(pack("grad", {k: p.grad for k, p in net.named_parameters() if p.grad is not None}))
+    blob.update(pack("gin", {k: v.grad for k, v in inputs.items() if v.grad is not None}))
+    blob.update(pack("sd_after", {k: v for k, v in net.state_dict().items() if "running" in k or "tracked" in k}))
+    if extra:
+        blob.update(extra)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **blob)
+    print("wrote", name, "out", tuple(out.shape))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    nw = R.load()
+
+    # ---- FCGANGenerator (networks.py:493-540): fcn (k4s2p1 first layer) and non-fcn (k4s1p0)
+    seed(1)
+    G = nw.define_G(2, 0, 4, "fcgan", "instance", False, n_layers_G=5, use_fcn=True, noise_nc=8, gpu_ids=[])
+    module_fixture("fcgan_G_fcn", G, {"z": torch.randn(2, 8, 1, 1)}, lambda n, z: n(z))
+    seed(2)
+    G = nw.define_G(2, 0, 4, "fcgan", "instance", False, n_layers_G=4, use_fcn=False, noise_nc=8, gpu_ids=[])
+    module_fixture("fcgan_G_nofcn", G, {"z": torch.randn(3, 8, 1, 1)}, lambda n, z: n(z))
+
+    # ---- NLayerDiscriminator (networks.py:798-847) at scale 1/2/4, BCE (sigmoid) and LSGAN (no sigmoid)
+    for s, nl, sig in ((1, 3, True), (2, 3, True), (4, 3, True), (1, 4, False), (2, 2, False)):
+        seed(10 + s + nl)
+        D = nw.define_D(2, 4, "n_layers", n_layers_D=nl, norm="instance", use_sigmoid=sig, scale_factor=R.sf(s), gpu_ids=[])
+        module_fixture("nlayerD_s%d_n%d_%s" % (s, nl, "sig" if sig else "lin"), D,
+                       {"x": torch.rand(2, 2, 96, 96) * 2 - 1}, lambda n, x: n(x))
+
+    # ---- UnetGenerator unet_128 (networks.py:318-419), instance norm, no dropout
+    seed(20)
+    U = nw.define_G(2, 1, 2, "unet_128", "instance", False, gpu_ids=[])
+    module_fixture("unet128", U, {"x": torch.rand(1, 2, 128, 128) * 2 - 1}, lambda n, x: n(x))
+    seed(21)
+    U = nw.define_G(1, 2, 2, "unet_256", "instance", False, gpu_ids=[])
+    module_fixture("unet256", U, {"x": torch.rand(1, 1, 256, 256) * 2 - 1}, lambda n, x: n(x))
+
+    # ---- CascadedRefinementNetwork (networks.py:642-794), both upsample modes
+    for mode, nb in (("bilinear", 2), ("convt", 1)):
+        seed(30 + nb)
+        C = nw.define_G(2, 1, 8, "crn", "instance", False, n_layers_G=5, noise_nc=8, upsample_mode=mode,
+                        n_layers_CRN_block=nb, gpu_ids=[])
+        module_fixture("crn_%s_b%d" % (mode, nb), C,
+                       {"label": torch.rand(1, 2, 64, 64) * 2 - 1, "noise": torch.randn(1, 8, 1, 1)},
+                       lambda n, label, noise: n(label, noise))
+
+    # ---- losses (networks.py:152-185, 205-214)
+    seed(40)
+    blob = {}
+    p = torch.rand(2, 1, 9, 9).clamp(1e-4, 1 - 1e-4).requires_grad_(True)
+    for lsgan in (False, True):
+        crit = nw.GANLoss(use_lsgan=lsgan, tensor=torch.FloatTensor)
+        for real in (True, False):
+            p.grad = None
+            l = crit(p, real)
+            l.backward()
+            tag = "%s_%s" % ("mse" if lsgan else "bce", "real" if real else "fake")
+            blob["out.loss_" + tag] = l.detach().numpy()
+            blob["out.grad_" + tag] = p.grad.numpy().copy()
+    blob["in.p"] = p.detach().numpy()
+    x = torch.randn(2, 1, 16, 16, requires_grad=True)
+    y = torch.randn(2, 1, 16, 16)
+    w = 1 + torch.rand(2, 1, 16, 16)
+    l1 = nw.WeightedL1Loss()
+    a = l1(x, y, w); a.backward(); blob["out.l1w"] = a.detach().numpy(); blob["out.l1w_grad"] = x.grad.numpy().copy(); x.grad = None
+    a = l1(x, y); a.backward(); blob["out.l1"] = a.detach().numpy(); blob["out.l1_grad"] = x.grad.numpy().copy()
+    blob.update({"in.x": x.detach().numpy(), "in.y": y.numpy(), "in.w": w.numpy()})
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **blob)
+    print("wrote losses")
+
+    # ---- gauss filter init (networks.py:22-40, 125-129)
+    blob = {}
+    for s in (2, 4):
+        D = nw.define_D(3, 4, "n_layers", n_layers_D=3, norm="instance", use_sigmoid=True, scale_factor=R.sf(s), gpu_ids=[])
+        blob["out.gauss_s%d" % s] = D.state_dict()["gauss_filter.0.weight"].numpy()
+    np.savez_compressed(os.path.join(OUT, "gauss.npz"), **blob)
+
+    # ---- full FCGANModel.optimize_parameters steps (fcgan_model.py:124-193), reduced widths
+    Model = R.load_model_class("fcgan")
+    for tag, B, pool, steps, lsgan, logd in (("bce_pool0", 2, 0, 3, False, True), ("bce_pool2", 1, 2, 5, False, True),
+                                             ("lsgan_nologd", 1, 0, 2, True, False)):
+        seed(100)
+        opt = R.fcgan_opt(batchSize=B, fineSize=64, noiseSize=1, ngf=4, ndf=4, pool_size=pool,
+                          no_lsgan=not lsgan, no_logD_trick=not logd)
+        m = Model()
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.initialize(opt)
+        blob = {}
+        blob.update(pack("sdG", m.netG.state_dict()))
+        for i, d in enumerate(m.netD):
+            blob.update(pack("sdD%d" % i, d.state_dict()))
+        random.seed(7)  # ImagePool draws from python `random`
+        for t in range(steps):
+            x = torch.rand(B, 3, 64, 64) * 2 - 1
+            m.set_input({"A": x, "A_paths": ["x"]})
+            m.optimize_parameters()
+            blob["in.real%d" % t] = m.real.detach().numpy().copy()
+            blob["in.noise%d" % t] = m.noise.detach().numpy().copy()
+            if t == 0:
+                blob["out.fake0"] = m.fake.detach().numpy().copy()
+            blob["out.loss%d" % t] = np.array([float(m.loss_G), float(m.loss_D_real), float(m.loss_D_fake)])
+            if t == 0:
+                blob.update(pack("gradG0", {k: p.grad for k, p in m.netG.named_parameters()}))
+        blob.update(pack("sdG_after", m.netG.state_dict()))
+        for i, d in enumerate(m.netD):
+            blob.update(pack("sdD%d_after" % i, d.state_dict()))
+        blob["meta.steps"] = np.array(steps)
+        np.savez_compressed(os.path.join(OUT, "fcgan_step_%s.npz" % tag), **blob)
+        print("wrote fcgan_step", tag, blob["out.loss%d" % (steps - 1)])
+
+
+if __name__ == "__main__":
+    main()
