@@ -1,0 +1,195 @@
+/*
+ * sgk.h -- C ABI of libsgk.so: hand-written sm_100a kernels for the supervised-gan
+ * adversarial-training hot path (one G+D update step through models/networks.py).
+ *
+ * What this boundary replaces: the reference has no native code; every primitive is a
+ * torch.nn module call in /root/reference/models/networks.py that bottoms out in
+ * ATen -> cuDNN / native CUDA kernels.  Each entry point below cites the reference
+ * call sites whose device work it takes over.  The host side (supervised-gan_b200/*.py)
+ * keeps the reference's Python surface (define_G / define_D / GANLoss / WeightedL1Loss,
+ * nn.Module forward/backward, state_dict layout) and calls these through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers
+ *     owned by the caller (allocated by the host framework's allocator); the library
+ *     never allocates or frees device memory on the hot path and keeps no pointer after
+ *     return.
+ *   - every call is asynchronous on the explicit `stream` (a cudaStream_t passed as
+ *     void*), performs no device synchronisation and no host read of device results, so
+ *     a whole training step is CUDA-graph capturable.
+ *   - return 0 on success, a negative SGK_E* code otherwise; sgk_last_error() returns a
+ *     thread-local message.  There is NO CPU fallback and no other backend.
+ *   - activations are fp32 NHWC ("channels last") inside a network; NCHW only at the
+ *     network edges (sgk_layout_*).  Weights are the reference's fp32 parameters
+ *     (Conv2d: OIHW, ConvTranspose2d: IOHW); kernels consume a packed K-major copy made
+ *     by sgk_conv_pack_weight.
+ */
+#ifndef SGK_H_
+#define SGK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGK_VERSION 1
+
+enum SgkStatus {
+  SGK_OK = 0,
+  SGK_EINVAL = -1,       /* bad shape / alignment / null pointer            */
+  SGK_EUNSUPPORTED = -2, /* outside the supported kernel family (no fallback) */
+  SGK_ECUDA = -3,        /* CUDA runtime / driver error (message has details) */
+  SGK_EWORKSPACE = -4    /* workspace too small                              */
+};
+
+enum SgkAct { SGK_ACT_NONE = 0, SGK_ACT_RELU = 1, SGK_ACT_LRELU = 2, SGK_ACT_TANH = 3, SGK_ACT_SIGMOID = 4 };
+
+/* arithmetic of the contraction */
+enum SgkPrecision {
+  SGK_FP32 = 0, /* CUDA-core FFMA, fp32 operands and accumulation (strict-parity mode)      */
+  SGK_TF32 = 1, /* tcgen05.mma kind::tf32, fp32 storage, fp32 accumulation in TMEM          */
+  SGK_BF16 = 2  /* tcgen05.mma kind::f16 on bf16 operands converted on load, fp32 accumulate */
+};
+
+/* which operator a packed weight / a launch is for */
+enum SgkConvOp { SGK_OP_FWD = 0, SGK_OP_DGRAD = 1, SGK_OP_WGRAD = 2 };
+
+/*
+ * One convolution layer, described in FORWARD terms.
+ *   transposed == 0 : nn.Conv2d          y[N,Cout,Hout,Wout] = conv(x[N,Cin,Hin,Win], w[Cout,Cin,kh,kw]) + b
+ *                     (networks.py:356,385 U-Net down; 686,752,774,781,787 CRN; 815,824,831,835 PatchGAN)
+ *   transposed == 1 : nn.ConvTranspose2d y = convT(x, w[Cin,Cout,kh,kw]) + b
+ *                     (networks.py:502-504,516,523,529 fcgan G; 357,392,398 U-Net up; 747 CRN convt)
+ * Hout/Wout must equal the PyTorch output size for (k, stride, pad); square kernels only.
+ */
+typedef struct SgkConvDesc {
+  int32_t N, Cin, Hin, Win;
+  int32_t Cout, Hout, Wout;
+  int32_t k, stride, pad;
+  int32_t transposed;
+  int32_t precision; /* enum SgkPrecision */
+} SgkConvDesc;
+
+int sgk_version(void);
+const char* sgk_last_error(void);
+/* number of SMs / compute capability of the current device (sanity check by the host side) */
+int sgk_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- convolution family */
+
+/* floats in the packed weight for `op` (SGK_OP_FWD or SGK_OP_DGRAD) */
+size_t sgk_conv_packed_weight_elems(const SgkConvDesc* d, int op);
+/* w_raw: reference-layout parameter; w_packed: K-major operand for `op`.  Called once per
+ * optimiser step per layer (weights only change in Adam). */
+int sgk_conv_pack_weight(const SgkConvDesc* d, int op, const float* w_raw, float* w_packed, void* stream);
+
+/* y = act(conv(x) + bias).  x, y NHWC.  bias may be NULL.  act: enum SgkAct (slope for LRELU). */
+int sgk_conv_fwd(const SgkConvDesc* d, const float* x, const float* w_packed_fwd, const float* bias,
+                 float* y, int act, float slope, void* stream);
+/* dx = conv^T(dy).  dy, dx NHWC.  (autograd of the sites above: aten::convolution_backward input grad) */
+int sgk_conv_dgrad(const SgkConvDesc* d, const float* dy, const float* w_packed_dgrad, float* dx, void* stream);
+/* dw (reference layout, OIHW / IOHW) = sum over pixels; split-K partials go to `workspace`
+ * and are reduced in a fixed order (deterministic).  x, dy NHWC.  dbias (may be NULL) = sum dy. */
+size_t sgk_conv_wgrad_workspace_bytes(const SgkConvDesc* d);
+int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float* dy, float* dw, float* dbias,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- layout (network edges) */
+int sgk_layout_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, void* stream);
+int sgk_layout_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------- normalisation + activation
+ * InstanceNorm2d(affine=False) (networks.py:47; sites 825,832 D; 387-389 U-Net; 687,754,775,782 CRN)
+ * and BatchNorm2d train mode (networks.py:87 -> 507,517,524) fused with the activation that follows.
+ * x, y NHWC.  `groups` = N for instance norm, 1 for batch norm (statistics over all N).
+ * stats: [groups*C*2] floats (mean, rstd) written by fwd, read by bwd.  gamma/beta NULL => no affine.
+ * running_mean/var (NULL to skip): momentum update with the unbiased variance.
+ * workspace: sgk_norm_workspace_bytes(). */
+size_t sgk_norm_workspace_bytes(int N, int C, int H, int W);
+int sgk_norm_act_fwd(const float* x, float* y, float* stats, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps,
+                     int N, int C, int H, int W, int per_sample, int act, float slope,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* dx from dy (gradient w.r.t. the activated output), the saved pre-norm x and stats.
+ * dgamma/dbeta (NULL when no affine) are written (not accumulated). */
+int sgk_norm_act_bwd(const float* dy, const float* x, const float* stats, const float* gamma, const float* beta,
+                     float* dx, float* dgamma, float* dbeta,
+                     int N, int C, int H, int W, int per_sample, int act, float slope,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- elementwise helpers */
+/* dx = dy * act'(.) given the activated output y (LRELU / RELU / TANH / SIGMOID) */
+int sgk_act_bwd(const float* dy, const float* y, float* dx, size_t n, int act, float slope, void* stream);
+/* y = act(x) (U-Net / CRN pre-activations, networks.py:386,388,773) */
+int sgk_act_fwd(const float* x, float* y, size_t n, int act, float slope, void* stream);
+/* db[c] = sum over rows of dy[rows, C] (NHWC bias gradient) */
+int sgk_bias_grad(const float* dy, float* db, size_t rows, int C, void* workspace, size_t workspace_bytes, void* stream);
+size_t sgk_bias_grad_workspace_bytes(size_t rows, int C);
+/* channel concat / split in NHWC (networks.py:417-419 U-Net skips, 713-733 CRN; cgan_model.py:162) */
+int sgk_concat2_nhwc(const float* a, int Ca, const float* b, int Cb, float* out, size_t pixels, void* stream);
+int sgk_split2_nhwc(const float* in, float* a, int Ca, float* b, int Cb, size_t pixels, void* stream);
+/* out = a + alpha * b */
+int sgk_axpy(const float* a, const float* b, float alpha, float* out, size_t n, void* stream);
+/* out = a * b (Dropout mask application, networks.py:403,518; the mask is drawn by the host framework's RNG) */
+int sgk_mul(const float* a, const float* b, float* out, size_t n, void* stream);
+/* out = x * (*alpha_dev): alpha is a DEVICE scalar (the 0-dim gradient flowing into a loss), no host sync */
+int sgk_scale_by_dev_scalar(const float* x, const float* alpha_dev, float* out, size_t n, void* stream);
+
+/* ---------------------------------------------------------------- resampling
+ * Discriminator pyramid (networks.py:807-813): channel-diagonal Gaussian blur k = 4*(s/2)+1,
+ * pad 2*(s/2), followed by AvgPool2d(1, stride=s) == decimation; only kept pixels are computed.
+ * taps: [C, k, k] floats = diagonal of gauss_filter.0.weight (host checks off-diagonals are 0). */
+int sgk_gauss_decimate_fwd(const float* x, const float* taps, float* y, int N, int C, int H, int W,
+                           int k, int scale, void* stream);
+int sgk_gauss_decimate_bwd(const float* dy, const float* taps, float* dx, int N, int C, int H, int W,
+                           int k, int scale, void* stream);
+/* nn.Upsample(scale_factor=2, mode='bilinear'), align_corners=False (networks.py:753; cgan_model.py:53) */
+int sgk_bilinear_up2_fwd(const float* x, float* y, int N, int C, int H, int W, void* stream);
+int sgk_bilinear_up2_bwd(const float* dy, float* dx, int N, int C, int H, int W, void* stream);
+/* nn.AvgPool2d(k, k) (networks.py:712-731; cgan_model.py:54) */
+int sgk_avgpool_fwd(const float* x, float* y, int N, int C, int H, int W, int k, void* stream);
+int sgk_avgpool_bwd(const float* dy, float* dx, int N, int C, int H, int W, int k, void* stream);
+
+/* ---------------------------------------------------------------- losses (forward value + gradient in one pass)
+ * GANLoss (networks.py:152-185): mode 0 = nn.BCELoss on probabilities (log clamp -100), 1 = nn.MSELoss,
+ * against the constant `target`.  loss_out[0] = mean loss; grad = d(loss)/d(pred) (unscaled; the autograd
+ * wrapper multiplies by the incoming gradient).  workspace: sgk_loss_workspace_bytes(n). */
+size_t sgk_loss_workspace_bytes(size_t n);
+int sgk_gan_loss(const float* pred, size_t n, int mode, float target, float* loss_out, float* grad,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* WeightedL1Loss (networks.py:205-214): mean(|x-y| * w), w may be NULL.  grad w.r.t. x. */
+int sgk_l1_loss(const float* x, const float* y, const float* w, size_t n, float* loss_out, float* grad,
+                void* workspace, size_t workspace_bytes, void* stream);
+/* BCELoss()((x+1)/2, (t+1)/2) (twostage_cycle_model.py:398-403).  grad w.r.t. x. */
+int sgk_bce_pair_loss(const float* x, const float* t, size_t n, float* loss_out, float* grad,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- optimiser
+ * torch.optim.Adam (fcgan_model.py:98-109; cgan_model.py:95-108; twostage_cycle_model.py:149-166):
+ * multi-tensor launches (metadata passed by value as kernel parameters, so a captured CUDA graph carries it).
+ *   tensors_host  HOST array of SgkAdamTensor (device pointers inside)
+ *   step_dev      device int64 step counter (steps taken so far); incremented by the call
+ *   hyper_dev     device float[5] = {lr, beta1, beta2, eps, grad_scale}; grad_scale folds the 1/world of
+ *                 data-parallel gradient averaging.  Device-resident so a captured CUDA graph stays valid
+ *                 when the host changes the learning rate (update_learning_rate, fcgan_model.py:228-236). */
+typedef struct SgkAdamTensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+} SgkAdamTensor;
+int sgk_adam_multi_tensor(const SgkAdamTensor* tensors_host, int n_tensors, int64_t* step_dev,
+                          const float* hyper_dev, void* stream);
+/* gathers / scatters a list of tensors into / from one flat buffer (gradient bucket for the data-parallel
+ * all-reduce); same by-value metadata scheme.  ptrs_host[i] has sizes_host[i] floats. */
+int sgk_multi_tensor_pack(const float* const* ptrs_host, const int64_t* sizes_host, int n_tensors, float* flat, void* stream);
+int sgk_multi_tensor_unpack(const float* flat, float* const* ptrs_host, const int64_t* sizes_host, int n_tensors, void* stream);
+int sgk_adam_block_elems(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGK_H_ */

@@ -1,0 +1,678 @@
+// fp32 CUDA-core implementation of the two generic conv problems (conv_plan.h):
+//   * gather_gemm_f : implicit-GEMM gather convolution (Conv fwd / dgrad, ConvT fwd / dgrad)
+//   * pixel_reduce_w: weight gradient (reduction over pixels, split across CTAs, ordered reduce)
+// This is the strict-parity (SGK_FP32) path and the path of the thin-channel layers, which are
+// HBM-bound by construction.  The tensor-bound layers go to conv_tc.cu (tcgen05).
+#include "conv_plan.h"
+
+namespace sgk {
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: raw [O][I][k][k] -> K-major operand of the gather GEMM
+//   direct     : Wp[O][(a,b,I)]
+//   transposed : Wp[ph][I][(a,b,O)] with raw tap r = r0 + rstep*a
+// ------------------------------------------------------------------------------------------------
+struct PackParams {
+  const float* raw;
+  float* packed;
+  int O, I, k;
+  int transposed_type;
+  int nphase;
+  GatherPhase ph[4];
+  long long total;
+};
+
+__global__ void pack_weight_kernel(const __grid_constant__ PackParams p) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.total) return;
+  int ph = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < p.nphase && idx >= p.ph[i].w_off) ph = i;
+  const GatherPhase& P = p.ph[ph];
+  long long local = idx - P.w_off;
+  int Cg = p.transposed_type ? p.O : p.I;  // gathered channel count (innermost)
+  int c = (int)(local % Cg);
+  long long t = local / Cg;
+  int b = (int)(t % P.tb);
+  t /= P.tb;
+  int a = (int)(t % P.ta);
+  int n = (int)(t / P.ta);
+  int ry = P.ry0 + P.rstep * a, rx = P.rx0 + P.rstep * b;
+  int o = p.transposed_type ? c : n;
+  int i = p.transposed_type ? n : c;
+  p.packed[idx] = p.raw[(((long long)o * p.I + i) * p.k + ry) * p.k + rx];
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather GEMM (F)
+// ------------------------------------------------------------------------------------------------
+struct FParams {
+  const float* in;
+  const float* w;
+  const float* bias;
+  float* out;
+  int N, Hi, Wi, Cg, Ho, Wo, Co;
+  int act;
+  float slope;
+  int nphase;
+  GatherPhase ph[4];
+};
+
+constexpr int F_BM = 128, F_BK = 16, F_THREADS = 256;
+
+template <int BN, bool VEC>
+__global__ void __launch_bounds__(F_THREADS) gather_gemm_f(const __grid_constant__ FParams p) {
+  constexpr int BM = F_BM, BK = F_BK;
+  constexpr int TM = 8, TN = BN / 16;
+  constexpr int LDA = BM + 4, LDB = BN + 4;
+  __shared__ __align__(16) float As[2][BK][LDA];
+  __shared__ __align__(16) float Bs[2][BK][LDB];
+
+  const int t = threadIdx.x;
+  // ---- which phase does this M tile belong to
+  int phi = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < p.nphase && (int)blockIdx.x >= p.ph[i].m_tile_begin) phi = i;
+  const GatherPhase P = p.ph[phi];
+  const int HWp = P.Hp * P.Wp;
+  const long long M = (long long)p.N * HWp;
+  const int K = P.ta * P.tb * p.Cg;
+  const long long m0 = (long long)(blockIdx.x - P.m_tile_begin) * BM;
+  const int n0 = blockIdx.y * BN;
+  const float* __restrict__ W = p.w + P.w_off;
+
+  // ---- A-load role: one row per thread, 8 consecutive k
+  const int arow = t & (BM - 1);
+  const int akh = (t >> 7) * 8;
+  long long am = m0 + arow;
+  bool arow_ok = am < M;
+  int an = 0, aiy0 = 0, aix0 = 0;
+  if (arow_ok) {
+    an = (int)(am / HWp);
+    int rem = (int)(am - (long long)an * HWp);
+    int oy = rem / P.Wp, ox = rem - oy * P.Wp;
+    aiy0 = oy * P.is + P.ioy;
+    aix0 = ox * P.is + P.iox;
+  }
+  const float* __restrict__ in_n = p.in + (long long)an * p.Hi * p.Wi * p.Cg;
+
+  // ---- B-load role
+  constexpr int B_F4 = BN * BK / 4;  // float4 slots
+  const int brow = t >> 2;           // output channel within tile
+  const int bkq = (t & 3) * 4;
+  const bool b_active = t < B_F4;
+  const int bco = n0 + brow;
+
+  float areg[8];
+  float breg[4];
+
+  auto load_tile = [&](int kt) {
+    const int kbase = kt * BK;
+    // A
+    if (VEC) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int k = kbase + akh + h * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (arow_ok && k < K) {
+          int tap = k / p.Cg;
+          int c = k - tap * p.Cg;
+          int a = tap / P.tb, b = tap - a * P.tb;
+          int iy = aiy0 + a, ix = aix0 + b;
+          if ((unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi)
+            v = __ldg(reinterpret_cast<const float4*>(in_n + ((long long)iy * p.Wi + ix) * p.Cg + c));
+        }
+        areg[h * 4 + 0] = v.x; areg[h * 4 + 1] = v.y; areg[h * 4 + 2] = v.z; areg[h * 4 + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int k = kbase + akh + i;
+        float v = 0.f;
+        if (arow_ok && k < K) {
+          int tap = k / p.Cg;
+          int c = k - tap * p.Cg;
+          int a = tap / P.tb, b = tap - a * P.tb;
+          int iy = aiy0 + a, ix = aix0 + b;
+          if ((unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi)
+            v = __ldg(in_n + ((long long)iy * p.Wi + ix) * p.Cg + c);
+        }
+        areg[i] = v;
+      }
+    }
+    // B
+    if (b_active) {
+      int k = kbase + bkq;
+      if (VEC) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bco < p.Co && k < K) v = __ldg(reinterpret_cast<const float4*>(W + (long long)bco * K + k));
+        breg[0] = v.x; breg[1] = v.y; breg[2] = v.z; breg[3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) breg[i] = (bco < p.Co && k + i < K) ? __ldg(W + (long long)bco * K + k + i) : 0.f;
+      }
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[buf][akh + i][arow] = areg[i];
+    if (b_active) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[buf][bkq + i][brow] = breg[i];
+    }
+  };
+
+  const int tx = t & 15, ty = t >> 4;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int KT = (K + BK - 1) / BK;
+  if (KT > 0) {
+    load_tile(0);
+    store_tile(0);
+  }
+  __syncthreads();
+  for (int kt = 0; kt < KT; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < KT) load_tile(kt + 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * TM]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * TM + 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      if (TN == 4) {
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * TN]);
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = Bs[buf][kk][tx * TN + j];
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < KT) store_tile(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias + activation, NHWC store
+  const int co0 = n0 + tx * TN;
+  float bv[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) bv[j] = (p.bias != nullptr && co0 + j < p.Co) ? __ldg(p.bias + co0 + j) : 0.f;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    long long m = m0 + ty * TM + i;
+    if (m >= M) continue;
+    int n = (int)(m / HWp);
+    int rem = (int)(m - (long long)n * HWp);
+    int oy = rem / P.Wp, ox = rem - oy * P.Wp;
+    float* o = p.out + (((long long)n * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co + co0;
+    float r[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) r[j] = act_apply(acc[i][j] + bv[j], p.act, p.slope);
+    if (TN == 4 && (p.Co & 3) == 0 && co0 + 3 < p.Co) {
+      *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < TN; ++j)
+        if (co0 + j < p.Co) o[j] = r[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// thin-output gather conv: Co <= 4.  One warp per output pixel, lanes split the K reduction with
+// coalesced float4 reads (NHWC keeps (b, c) contiguous for a fixed tap row), warp-shuffle reduce.
+// Used by the last PatchGAN conv (Cout = 1) and the generators' last ConvT (Cout = 1/2).
+// ------------------------------------------------------------------------------------------------
+template <int CO>
+__global__ void __launch_bounds__(256) gather_thin_out(const __grid_constant__ FParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // phase lookup by pixel prefix (m_tile_begin is reused as pixel-prefix / 8 warps... see launcher)
+  int phi = 0;
+  long long base = 0;
+  {
+    long long acc_pix = 0;
+    for (int i = 0; i < p.nphase; ++i) {
+      long long cnt = (long long)p.N * p.ph[i].Hp * p.ph[i].Wp;
+      if (warp >= acc_pix && warp < acc_pix + cnt) { phi = i; base = acc_pix; }
+      acc_pix += cnt;
+    }
+    if (warp >= acc_pix) return;
+  }
+  const GatherPhase P = p.ph[phi];
+  const int HWp = P.Hp * P.Wp;
+  long long m = warp - base;
+  int n = (int)(m / HWp);
+  int rem = (int)(m - (long long)n * HWp);
+  int oy = rem / P.Wp, ox = rem - oy * P.Wp;
+  int iy0 = oy * P.is + P.ioy, ix0 = ox * P.is + P.iox;
+  const int rowlen = P.tb * p.Cg;  // contiguous floats of one tap row (when fully inside)
+  const int K = P.ta * rowlen;
+  const float* __restrict__ W = p.w + P.w_off;
+  const float* __restrict__ in_n = p.in + (long long)n * p.Hi * p.Wi * p.Cg;
+  float acc[CO];
+#pragma unroll
+  for (int j = 0; j < CO; ++j) acc[j] = 0.f;
+  const bool vec = (p.Cg & 3) == 0;
+  for (int a = 0; a < P.ta; ++a) {
+    int iy = iy0 + a;
+    if ((unsigned)iy >= (unsigned)p.Hi) continue;
+    const float* __restrict__ row = in_n + ((long long)iy * p.Wi + ix0) * p.Cg;
+    if (vec) {
+      for (int e = lane * 4; e < rowlen; e += 128) {
+        int b = e / p.Cg;
+        int ix = ix0 + b;
+        if ((unsigned)ix >= (unsigned)p.Wi) continue;
+        float4 v = __ldg(reinterpret_cast<const float4*>(row + e));
+#pragma unroll
+        for (int j = 0; j < CO; ++j) {
+          if (j < p.Co) {
+            float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)j * K + a * rowlen + e));
+            acc[j] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[j]))));
+          }
+        }
+      }
+    } else {
+      for (int e = lane; e < rowlen; e += 32) {
+        int b = e / p.Cg;
+        int ix = ix0 + b;
+        if ((unsigned)ix >= (unsigned)p.Wi) continue;
+        float v = __ldg(row + e);
+#pragma unroll
+        for (int j = 0; j < CO; ++j)
+          if (j < p.Co) acc[j] = fmaf(v, __ldg(W + (long long)j * K + a * rowlen + e), acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CO; ++j) acc[j] = warp_sum(acc[j]);
+  if (lane == 0) {
+    float* o = p.out + (((long long)n * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co;
+#pragma unroll
+    for (int j = 0; j < CO; ++j)
+      if (j < p.Co) o[j] = act_apply(acc[j] + (p.bias ? __ldg(p.bias + j) : 0.f), p.act, p.slope);
+  }
+}
+
+static int launch_gather(const GatherPlan& g, const float* in, const float* w, const float* bias, float* out, int act,
+                         float slope, cudaStream_t st) {
+  FParams p{};
+  p.in = in; p.w = w; p.bias = bias; p.out = out;
+  p.N = g.N; p.Hi = g.Hi; p.Wi = g.Wi; p.Cg = g.Cg; p.Ho = g.Ho; p.Wo = g.Wo; p.Co = g.Co;
+  p.act = act; p.slope = slope; p.nphase = g.nphase;
+  long long tiles = 0, pixels = 0;
+  for (int i = 0; i < g.nphase; ++i) {
+    p.ph[i] = g.ph[i];
+    p.ph[i].m_tile_begin = (int)tiles;
+    long long M = (long long)g.N * g.ph[i].Hp * g.ph[i].Wp;
+    tiles += ceil_div64(M, F_BM);
+    pixels += M;
+  }
+  if (pixels == 0) return SGK_OK;
+  if (g.Co <= 4) {
+    long long threads = pixels * 32;
+    long long blocks = ceil_div64(threads, 256);
+    if (blocks > 0x7fffffffLL) { set_error("conv: grid too large"); return SGK_EUNSUPPORTED; }
+    if (g.Co <= 1) gather_thin_out<1><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else if (g.Co == 2) gather_thin_out<2><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else gather_thin_out<4><<<(unsigned)blocks, 256, 0, st>>>(p);
+    SGK_LAUNCH_CHECK("gather_thin_out");
+    return SGK_OK;
+  }
+  if (tiles > 0x7fffffffLL) { set_error("conv: grid too large"); return SGK_EUNSUPPORTED; }
+  bool vec = (g.Cg % 4) == 0;
+  if (g.Co > 32) {
+    dim3 grid((unsigned)tiles, (unsigned)ceil_div(g.Co, 64));
+    if (vec) gather_gemm_f<64, true><<<grid, F_THREADS, 0, st>>>(p);
+    else gather_gemm_f<64, false><<<grid, F_THREADS, 0, st>>>(p);
+  } else {
+    dim3 grid((unsigned)tiles, (unsigned)ceil_div(g.Co, 32));
+    if (vec) gather_gemm_f<32, true><<<grid, F_THREADS, 0, st>>>(p);
+    else gather_gemm_f<32, false><<<grid, F_THREADS, 0, st>>>(p);
+  }
+  SGK_LAUNCH_CHECK("gather_gemm_f");
+  return SGK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient (W): dWp[m][(a,b,c)] = sum_pixels G[pix][m] * X[gather(pix,a,b)][c]
+// ------------------------------------------------------------------------------------------------
+struct WParams {
+  const float* g;
+  const float* x;
+  float* part;  // [splits][Cm][K]
+  int N, Hg, Wg, Cm;
+  int Hx, Wx, Cx;
+  int k, s, off;
+  int K;
+  long long P;            // pixels
+  long long p_per_split;  // multiple of 16
+};
+
+constexpr int W_BM = 64, W_BN = 64, W_BP = 16;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) pixel_reduce_w(const __grid_constant__ WParams p) {
+  constexpr int LD = 64 + 4;
+  __shared__ __align__(16) float Gs[2][W_BP][LD];
+  __shared__ __align__(16) float Xs[2][W_BP][LD];
+  const int t = threadIdx.x;
+  const int j0 = blockIdx.x * W_BN;  // k-columns
+  const int mch0 = blockIdx.y * W_BM;
+  const long long pbeg = (long long)blockIdx.z * p.p_per_split;
+  long long pend = pbeg + p.p_per_split;
+  if (pend > p.P) pend = p.P;
+  const int HWg = p.Hg * p.Wg;
+
+  const int lp = t >> 4;          // pixel within step
+  const int l4 = (t & 15) * 4;    // 4 consecutive channels / columns
+  // column decode (fixed for the whole CTA lifetime)
+  int ca[4], cb[4], cc[4];
+  bool cok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int j = j0 + l4 + i;
+    cok[i] = j < p.K;
+    int tap = cok[i] ? j / p.Cx : 0;
+    cc[i] = cok[i] ? j - tap * p.Cx : 0;
+    ca[i] = tap / p.k;
+    cb[i] = tap - ca[i] * p.k;
+  }
+  float greg[4], xreg[4];
+  auto load_step = [&](long long q0) {
+    long long q = q0 + lp;
+    bool ok = q < pend;
+    int n = 0, oy = 0, ox = 0;
+    if (ok) {
+      n = (int)(q / HWg);
+      int rem = (int)(q - (long long)n * HWg);
+      oy = rem / p.Wg;
+      ox = rem - oy * p.Wg;
+    }
+    // G
+    {
+      const float* gp = p.g + q * p.Cm + mch0 + l4;
+      if (VEC) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && mch0 + l4 < p.Cm) v = __ldg(reinterpret_cast<const float4*>(gp));
+        greg[0] = v.x; greg[1] = v.y; greg[2] = v.z; greg[3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) greg[i] = (ok && mch0 + l4 + i < p.Cm) ? __ldg(gp + i) : 0.f;
+      }
+    }
+    // X gather
+    const float* xn = p.x + (long long)n * p.Hx * p.Wx * p.Cx;
+    if (VEC) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && cok[0]) {
+        int iy = oy * p.s + ca[0] + p.off, ix = ox * p.s + cb[0] + p.off;
+        if ((unsigned)iy < (unsigned)p.Hx && (unsigned)ix < (unsigned)p.Wx)
+          v = __ldg(reinterpret_cast<const float4*>(xn + ((long long)iy * p.Wx + ix) * p.Cx + cc[0]));
+      }
+      xreg[0] = v.x; xreg[1] = v.y; xreg[2] = v.z; xreg[3] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = 0.f;
+        if (ok && cok[i]) {
+          int iy = oy * p.s + ca[i] + p.off, ix = ox * p.s + cb[i] + p.off;
+          if ((unsigned)iy < (unsigned)p.Hx && (unsigned)ix < (unsigned)p.Wx)
+            v = __ldg(xn + ((long long)iy * p.Wx + ix) * p.Cx + cc[i]);
+        }
+        xreg[i] = v;
+      }
+    }
+  };
+  auto store_step = [&](int buf) {
+    *reinterpret_cast<float4*>(&Gs[buf][lp][l4]) = make_float4(greg[0], greg[1], greg[2], greg[3]);
+    *reinterpret_cast<float4*>(&Xs[buf][lp][l4]) = make_float4(xreg[0], xreg[1], xreg[2], xreg[3]);
+  };
+
+  const int tx = t & 15, ty = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const long long steps = (pend > pbeg) ? (pend - pbeg + W_BP - 1) / W_BP : 0;
+  if (steps > 0) {
+    load_step(pbeg);
+    store_step(0);
+  }
+  __syncthreads();
+  for (long long sidx = 0; sidx < steps; ++sidx) {
+    const int buf = (int)(sidx & 1);
+    if (sidx + 1 < steps) load_step(pbeg + (sidx + 1) * W_BP);
+#pragma unroll
+    for (int pp = 0; pp < W_BP; ++pp) {
+      float4 a = *reinterpret_cast<const float4*>(&Gs[buf][pp][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Xs[buf][pp][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bw[j], acc[i][j]);
+    }
+    if (sidx + 1 < steps) store_step(buf ^ 1);
+    __syncthreads();
+  }
+  float* part = p.part + (long long)blockIdx.z * p.Cm * p.K;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = mch0 + ty * 4 + i;
+    if (m >= p.Cm) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = j0 + tx * 4 + j;
+      if (col < p.K) part[(long long)m * p.K + col] = acc[i][j];
+    }
+  }
+}
+
+// thin-M weight gradient (Cm <= 2): dW[m][col] = sum_pix g[pix][m] * X[gather][col].
+// Each thread owns 4 consecutive columns; a CTA walks a pixel chunk.
+struct WThinParams {
+  WParams w;
+};
+template <int CM>
+__global__ void __launch_bounds__(256) pixel_reduce_w_thin(const __grid_constant__ WParams p) {
+  const int j = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const long long pbeg = (long long)blockIdx.z * p.p_per_split;
+  long long pend = pbeg + p.p_per_split;
+  if (pend > p.P) pend = p.P;
+  if (j >= p.K) return;
+  const int HWg = p.Hg * p.Wg;
+  int tap = j / p.Cx;
+  const int c = j - tap * p.Cx;
+  const int a = tap / p.k, b = tap - a * p.k;
+  float acc[CM][4];
+#pragma unroll
+  for (int m = 0; m < CM; ++m)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
+  int n = (int)(pbeg / HWg);
+  int rem = (int)(pbeg - (long long)n * HWg);
+  int oy = rem / p.Wg, ox = rem - oy * p.Wg;
+  for (long long q = pbeg; q < pend; ++q) {
+    int iy = oy * p.s + a + p.off, ix = ox * p.s + b + p.off;
+    if ((unsigned)iy < (unsigned)p.Hx && (unsigned)ix < (unsigned)p.Wx) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(p.x + (((long long)n * p.Hx + iy) * p.Wx + ix) * p.Cx + c));
+#pragma unroll
+      for (int m = 0; m < CM; ++m) {
+        float gv = __ldg(p.g + q * p.Cm + m);
+        acc[m][0] = fmaf(gv, v.x, acc[m][0]);
+        acc[m][1] = fmaf(gv, v.y, acc[m][1]);
+        acc[m][2] = fmaf(gv, v.z, acc[m][2]);
+        acc[m][3] = fmaf(gv, v.w, acc[m][3]);
+      }
+    }
+    if (++ox == p.Wg) { ox = 0; if (++oy == p.Hg) { oy = 0; ++n; } }
+  }
+  float* part = p.part + (long long)blockIdx.z * p.Cm * p.K;
+#pragma unroll
+  for (int m = 0; m < CM; ++m)
+    *reinterpret_cast<float4*>(part + (long long)m * p.K + j) = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
+}
+
+// ordered reduction over splits and scatter into the reference layout raw[O][I][k][k]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int O, int I, int k, int splits) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)O * I * k * k;
+  if (idx >= total) return;
+  // idx enumerates the packed order [o][(a,b,i)] so reads are coalesced
+  int i = (int)(idx % I);
+  long long tt = idx / I;
+  int b = (int)(tt % k);
+  tt /= k;
+  int a = (int)(tt % k);
+  int o = (int)(tt / k);
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += part[(long long)sp * total + idx];
+  dw[(((long long)o * I + i) * k + a) * k + b] = s;
+}
+
+static void wgrad_split_plan(const EquivConv& e, int* splits, long long* p_per_split) {
+  long long P = (long long)e.N * e.Hs * e.Ws;
+  long long K = (long long)e.k * e.k * e.I;
+  long long tiles = (e.O <= 2) ? ceil_div64(K, 1024) : ceil_div64(e.O, W_BM) * ceil_div64(K, W_BN);
+  long long target = 4LL * sm_count();
+  long long s = ceil_div64(target, tiles);
+  long long min_pix = (e.O <= 2) ? 64 : 256;
+  long long max_s = ceil_div64(P, min_pix);
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  if (s > 512) s = 512;
+  long long pps = ceil_div64(ceil_div64(P, s), W_BP) * W_BP;
+  s = ceil_div64(P, pps);
+  *splits = (int)s;
+  *p_per_split = pps;
+}
+
+}  // namespace sgk
+
+using namespace sgk;
+
+extern "C" size_t sgk_conv_packed_weight_elems(const SgkConvDesc* d, int op) {
+  if (!d || validate_desc(*d) != 0 || (op != SGK_OP_FWD && op != SGK_OP_DGRAD)) return 0;
+  return (size_t)make_gather_plan(*d, op).packed_elems;
+}
+
+extern "C" int sgk_conv_pack_weight(const SgkConvDesc* d, int op, const float* w_raw, float* w_packed, void* stream) {
+  SGK_CHECK_ARG(d && w_raw && w_packed, "sgk_conv_pack_weight: null argument");
+  SGK_CHECK_ARG(op == SGK_OP_FWD || op == SGK_OP_DGRAD, "sgk_conv_pack_weight: op must be FWD or DGRAD");
+  int rc = validate_desc(*d);
+  if (rc) return rc;
+  GatherPlan g = make_gather_plan(*d, op);
+  PackParams p{};
+  p.raw = w_raw; p.packed = w_packed; p.O = g.O; p.I = g.I; p.k = g.k;
+  p.transposed_type = g.transposed_type; p.nphase = g.nphase; p.total = g.packed_elems;
+  for (int i = 0; i < g.nphase; ++i) p.ph[i] = g.ph[i];
+  if (p.total == 0) return SGK_OK;
+  pack_weight_kernel<<<(unsigned)ceil_div64(p.total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  SGK_LAUNCH_CHECK("pack_weight_kernel");
+  return SGK_OK;
+}
+
+namespace sgk {
+int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, const float* w, const float* bias, float* out,
+                int act, float slope, cudaStream_t st);  // conv_tc.cu; returns SGK_EUNSUPPORTED if shape not covered
+int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+}
+
+static int conv_gather_dispatch(const SgkConvDesc* d, int op, const float* in, const float* w, const float* bias,
+                                float* out, int act, float slope, void* stream) {
+  SGK_CHECK_ARG(d && in && w && out, "sgk_conv: null argument");
+  int rc = validate_desc(*d);
+  if (rc) return rc;
+  GatherPlan g = make_gather_plan(*d, op);
+  if (d->precision != SGK_FP32) {
+    rc = conv_fwd_tc(d, g, in, w, bias, out, act, slope, (cudaStream_t)stream);
+    if (rc != SGK_EUNSUPPORTED) return rc;
+    // thin-channel problems are HBM-bound and stay on the CUDA-core kernels by design
+  }
+  return launch_gather(g, in, w, bias, out, act, slope, (cudaStream_t)stream);
+}
+
+extern "C" int sgk_conv_fwd(const SgkConvDesc* d, const float* x, const float* w_packed_fwd, const float* bias, float* y,
+                            int act, float slope, void* stream) {
+  return conv_gather_dispatch(d, SGK_OP_FWD, x, w_packed_fwd, bias, y, act, slope, stream);
+}
+
+extern "C" int sgk_conv_dgrad(const SgkConvDesc* d, const float* dy, const float* w_packed_dgrad, float* dx, void* stream) {
+  return conv_gather_dispatch(d, SGK_OP_DGRAD, dy, w_packed_dgrad, nullptr, dx, SGK_ACT_NONE, 0.f, stream);
+}
+
+extern "C" size_t sgk_conv_wgrad_workspace_bytes(const SgkConvDesc* d) {
+  if (!d || validate_desc(*d) != 0) return 0;
+  EquivConv e = equiv_conv(*d);
+  int splits;
+  long long pps;
+  wgrad_split_plan(e, &splits, &pps);
+  size_t a = (size_t)splits * e.O * e.I * e.k * e.k * sizeof(float);
+  size_t b = sgk_bias_grad_workspace_bytes((size_t)d->N * d->Hout * d->Wout, d->Cout);
+  return a > b ? a : b;
+}
+
+extern "C" int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float* dy, float* dw, float* dbias,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  SGK_CHECK_ARG(d && x && dy && dw && workspace, "sgk_conv_wgrad: null argument");
+  int rc = validate_desc(*d);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  EquivConv e = equiv_conv(*d);
+  if (dbias) {
+    // db = column sums of dy (the forward OUTPUT gradient) -- separate reduction over [pixels, Cout]
+    size_t rows = (size_t)d->N * d->Hout * d->Wout;
+    size_t need = sgk_bias_grad_workspace_bytes(rows, d->Cout);
+    if (need > workspace_bytes) { set_error("sgk_conv_wgrad: workspace too small for bias grad"); return SGK_EWORKSPACE; }
+    rc = sgk_bias_grad(dy, dbias, rows, d->Cout, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  if (d->precision != SGK_FP32) {
+    rc = conv_wgrad_tc(d, x, dy, dw, workspace, workspace_bytes, st);
+    if (rc != SGK_EUNSUPPORTED) return rc;
+  }
+  int splits;
+  long long pps;
+  wgrad_split_plan(e, &splits, &pps);
+  size_t need = (size_t)splits * e.O * e.I * e.k * e.k * sizeof(float);
+  if (need > workspace_bytes) { set_error("sgk_conv_wgrad: workspace %zu < %zu", workspace_bytes, need); return SGK_EWORKSPACE; }
+  WParams p{};
+  // G = O-side tensor (small grid), X = I-side tensor (big grid)
+  p.g = d->transposed ? x : dy;
+  p.x = d->transposed ? dy : x;
+  p.part = (float*)workspace;
+  p.N = e.N; p.Hg = e.Hs; p.Wg = e.Ws; p.Cm = e.O; p.Hx = e.Hb; p.Wx = e.Wb; p.Cx = e.I;
+  p.k = e.k; p.s = e.s; p.off = -e.p; p.K = e.k * e.k * e.I;
+  p.P = (long long)e.N * e.Hs * e.Ws; p.p_per_split = pps;
+  if (e.O <= 2 && (e.I % 4) == 0) {
+    dim3 grid((unsigned)ceil_div(p.K, 1024), 1, (unsigned)splits);
+    if (e.O == 1) pixel_reduce_w_thin<1><<<grid, 256, 0, st>>>(p);
+    else pixel_reduce_w_thin<2><<<grid, 256, 0, st>>>(p);
+    SGK_LAUNCH_CHECK("pixel_reduce_w_thin");
+  } else {
+    dim3 grid((unsigned)ceil_div(p.K, W_BN), (unsigned)ceil_div(e.O, W_BM), (unsigned)splits);
+    bool vec = (e.I % 4) == 0 && (e.O % 4) == 0;
+    if (vec) pixel_reduce_w<true><<<grid, 256, 0, st>>>(p);
+    else pixel_reduce_w<false><<<grid, 256, 0, st>>>(p);
+    SGK_LAUNCH_CHECK("pixel_reduce_w");
+  }
+  long long total = (long long)e.O * e.I * e.k * e.k;
+  wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>((const float*)workspace, dw, e.O, e.I, e.k, splits);
+  SGK_LAUNCH_CHECK("wgrad_reduce_kernel");
+  return SGK_OK;
+}

@@ -1,0 +1,223 @@
+"""Step driver of the unconditional multi-scale GAN: same interface, option names, pass order, detach
+points and loss weights as the reference's models/fcgan_model.py:28-236 (FCGANModel), running on the
+libsgk kernels through `networks`.
+
+Differences that do not change any consumed result (all switchable, see DESIGN.md "deviations"):
+  * opt.batch_D_passes (default True): D(fake.detach()) and D(real) run as ONE 2B-batch pass -- exact for
+    the InstanceNorm discriminators (no cross-sample coupling) -- halving launches and doubling GEMM-M.
+  * opt.skip_unused_grads (default True): while back-propagating loss_G, D parameters do not require grad,
+    so the D weight gradients the reference computes and then discards (zero_grad at the next step) are
+    never computed.
+  * the optimisers are FusedAdam (one multi-tensor kernel) instead of torch.optim.Adam; same update rule.
+"""
+import itertools
+import os
+from collections import OrderedDict
+
+import torch
+
+from . import networks, ops
+from .image_pool import ImagePool
+from .optim import FusedAdam
+
+
+class FCGANModel(object):
+    def name(self):
+        return 'FCGANModel'
+
+    def initialize(self, opt):
+        # base_model.py:9-16
+        self.opt = opt
+        self.gpu_ids = opt.gpu_ids
+        self.isTrain = opt.isTrain
+        if not self.gpu_ids or not torch.cuda.is_available():
+            raise RuntimeError("supervised-gan_b200 runs on CUDA only: pass gpu_ids=[<device>] (no CPU fallback)")
+        self.device = torch.device("cuda", self.gpu_ids[0])
+        self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
+        self.model_dir = getattr(opt, "pretrained_model_dir", "")
+
+        # parse which_channel (fcgan_model.py:47-58)
+        idx_dict = {'r': 0, 'g': 1, 'b': 2}
+        self.chnl_idx_input = []
+        self.chnl_idx_visual = []
+        for s in opt.which_channel.split('_'):
+            self.chnl_idx_visual.append([idx_dict[c] for c in s])
+            self.chnl_idx_input += [idx_dict[c] for c in s]
+        self.chnl_idx_input = torch.tensor(self.chnl_idx_input, dtype=torch.long)
+        opt.input_nc = len(self.chnl_idx_input)
+
+        dev = self.device
+        self.input = torch.empty(opt.batchSize, opt.input_nc, opt.fineSize, opt.fineSize, device=dev)
+        self.noise = None
+        self.noise_ = torch.empty(opt.batchSize, opt.noise_nc, opt.noiseSize, opt.noiseSize, device=dev)
+        self.fixed_noiseA = torch.empty_like(self.noise_).normal_(0, 1)
+        self.fixed_noiseB = torch.empty_like(self.noise_).normal_(0, 1)
+
+        self.netG = networks.define_G(opt.input_nc, 0, opt.ngf, opt.which_model_netG, opt.norm, not opt.no_dropout,
+                                      n_layers_G=opt.n_layers_G, use_residual=opt.use_residual,
+                                      use_fcn=opt.noiseSize != 1, noise_nc=opt.noise_nc,
+                                      add_gaussian_noise=opt.add_gaussian_noise, gaussian_sigma=opt.gaussian_sigma,
+                                      upsample_mode=opt.upsample_mode, n_layers_CRN_block=opt.n_layers_CRN_block,
+                                      share_label_weights=not opt.no_share_label_block_weights, gpu_ids=self.gpu_ids)
+        if self.isTrain:
+            use_sigmoid = opt.no_lsgan
+            assert (len(opt.scale_factor) == len(opt.lambda_D) == len(opt.n_layers_D))
+            self.n_netD = len(opt.scale_factor)
+            self.netD = []
+            for scale, n_layers in zip(opt.scale_factor, opt.n_layers_D):
+                self.netD.append(networks.define_D(opt.input_nc, opt.ndf, opt.which_model_netD, n_layers_D=n_layers,
+                                                   norm=opt.norm, use_sigmoid=use_sigmoid, scale_factor=scale,
+                                                   gpu_ids=self.gpu_ids))
+        if not self.isTrain or opt.continue_train:
+            self.load_network(self.netG, 'G', opt.which_epoch)
+            if self.isTrain:
+                for netD, n in zip(self.netD, range(self.n_netD)):
+                    self.load_network(netD, 'D_%d' % n, opt.which_epoch)
+
+        if self.isTrain:
+            self.fake_pool = ImagePool(opt.pool_size)
+            self.old_lr = opt.lr
+            self.criterionGAN = networks.GANLoss(use_lsgan=not opt.no_lsgan)
+            grad_scale = getattr(opt, "grad_scale", 1.0)
+            self.optimizer_G = FusedAdam(self.netG.parameters(), lr=opt.lr, betas=(opt.beta1, 0.999),
+                                         grad_scale=grad_scale)
+            # all learnable D parameters live in netD.model; gauss_filter is fixed (fcgan_model.py:100-109)
+            params = itertools.chain(*[netD.model.parameters() for netD in self.netD])
+            self.optimizer_D = FusedAdam(params, lr=opt.lr, betas=(opt.beta1, 0.999), grad_scale=grad_scale)
+            self.params_D = [p for netD in self.netD for p in netD.model.parameters()]
+            self.params_G = list(self.netG.parameters())
+        self.batch_D_passes = getattr(opt, "batch_D_passes", True) and opt.norm == 'instance'
+        self.skip_unused_grads = getattr(opt, "skip_unused_grads", True)
+        self.grad_sync = None  # data-parallel hook: callable(list_of_params, tag) run between backward and step
+
+    # ------------------------------------------------------------------ data
+    def set_input(self, input):
+        AorB = self.opt.which_direction == 'A'
+        data = input['A' if AorB else 'B'].index_select(1, self.chnl_idx_input)
+        if self.input.shape != data.shape:
+            self.input = torch.empty(data.shape, device=self.device)
+        self.input.copy_(data, non_blocking=True)
+        self.image_paths = input['A_paths' if AorB else 'B_paths']
+
+    def _draw_noise(self):
+        o = self.opt
+        if self.noise_.shape != (o.batchSize, o.noise_nc, o.noiseSize, o.noiseSize):
+            self.noise_ = torch.empty(o.batchSize, o.noise_nc, o.noiseSize, o.noiseSize, device=self.device)
+        return self.noise_.normal_(0, 1)
+
+    def forward(self):
+        self.real = self.input
+        self.noise = self._draw_noise()
+        self.fake = self.netG.forward(self.noise)
+
+    def sample_noise(self):
+        self.noise = self._draw_noise()
+        self.fake = self.netG.forward(self.noise)
+
+    def test(self):
+        with torch.no_grad():
+            self.noise = self._draw_noise()
+            self.fake = self.netG.forward(self.noise)
+
+    def get_image_paths(self):
+        return self.image_paths
+
+    # ------------------------------------------------------------------ the two phases (fcgan_model.py:146-176)
+    def backward_D(self):
+        fake = self.fake_pool.query(self.fake)
+        real = self.real
+        self.loss_D_fake = 0
+        self.loss_D_real = 0
+        if self.batch_D_passes and fake.shape == real.shape:
+            both = torch.cat([fake.detach(), real], 0)
+            B = fake.shape[0]
+            for netD in self.netD:
+                pred = netD.forward(both)
+                self.loss_D_fake = self.loss_D_fake + self.criterionGAN(pred[:B], False)
+                self.loss_D_real = self.loss_D_real + self.criterionGAN(pred[B:], True)
+        else:
+            for netD in self.netD:
+                self.loss_D_fake = self.loss_D_fake + self.criterionGAN(netD.forward(fake.detach()), False)
+            for netD in self.netD:
+                self.loss_D_real = self.loss_D_real + self.criterionGAN(netD.forward(real), True)
+        self.loss_D = (self.loss_D_fake + self.loss_D_real) * 0.5
+        self.loss_D.backward()
+
+    def backward_G(self):
+        fake = self.fake
+        self.loss_G = 0
+        if self.skip_unused_grads:
+            for p in self.params_D:
+                p.requires_grad_(False)
+        try:
+            for netD, lambda_D in zip(self.netD, self.opt.lambda_D):
+                pred_fake = netD.forward(fake)
+                if not self.opt.no_logD_trick:
+                    self.loss_G = self.loss_G + self.criterionGAN(pred_fake, True) * lambda_D
+                else:
+                    self.loss_G = self.loss_G + -self.criterionGAN(pred_fake, False) * lambda_D
+            self.loss_G.backward()
+        finally:
+            if self.skip_unused_grads:
+                for p in self.params_D:
+                    p.requires_grad_(True)
+
+    def optimize_parameters(self):
+        self.forward()
+        for _ in range(self.opt.n_update_D):
+            self.optimizer_D.zero_grad(set_to_none=True)
+            self.backward_D()
+            if self.grad_sync is not None:
+                self.grad_sync(self.params_D, "D")
+            self.optimizer_D.step()
+            if self.opt.n_update_D > 1:
+                self.sample_noise()
+        for _ in range(self.opt.n_update_G):
+            self.optimizer_G.zero_grad(set_to_none=True)
+            self.backward_G()
+            if self.grad_sync is not None:
+                self.grad_sync(self.params_G, "G")
+            self.optimizer_G.step()
+            if self.opt.n_update_G > 1:
+                self.sample_noise()
+
+    # ------------------------------------------------------------------ reporting / checkpoints
+    def get_current_errors(self):
+        # reference reads loss.data[0] (fcgan_model.py:195-199); one D2H sync per value, only when printing
+        return OrderedDict([('G_GAN', float(self.loss_G)), ('D_real', float(self.loss_D_real)),
+                            ('D_fake', float(self.loss_D_fake))])
+
+    def get_current_visuals(self, save_real=False, save_as_single_image=True):
+        out = OrderedDict()
+        if self.isTrain or save_real:
+            out['real'] = self.real.detach()
+        out['fake'] = self.fake.detach()
+        return out
+
+    def save_network(self, network, network_label, epoch_label, gpu_ids=[], model_dir=''):
+        # base_model.py:44-52: reference-compatible '<epoch>_net_<label>.pth' holding a CPU state_dict
+        save_filename = '%s_net_%s.pth' % (epoch_label, network_label)
+        save_path = os.path.join(model_dir or self.save_dir, save_filename)
+        os.makedirs(os.path.dirname(save_path), exist_ok=True)
+        torch.save({k: v.detach().cpu() for k, v in network.state_dict().items()}, save_path)
+
+    def load_network(self, network, network_label, epoch_label, model_dir=''):
+        save_filename = '%s_net_%s.pth' % (epoch_label, network_label)
+        save_path = os.path.join(model_dir or self.save_dir, save_filename)
+        network.load_state_dict(torch.load(save_path, map_location=self.device))
+        ops.bump_weights_epoch()
+
+    def save(self, label):
+        self.save_network(self.netG, 'G', label, gpu_ids=self.gpu_ids)
+        for netD, n in zip(self.netD, range(self.n_netD)):
+            self.save_network(netD, 'D_%d' % n, label, self.gpu_ids)
+
+    def update_learning_rate(self):
+        lrd = self.opt.lr / self.opt.niter_decay
+        lr = self.old_lr - lrd
+        for param_group in self.optimizer_D.param_groups:
+            param_group['lr'] = lr
+        for param_group in self.optimizer_G.param_groups:
+            param_group['lr'] = lr
+        print('update learning rate: %f -> %f' % (self.old_lr, lr))
+        self.old_lr = lr

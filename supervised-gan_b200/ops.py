@@ -1,0 +1,490 @@
+"""torch.autograd bindings of the libsgk kernels (include/sgk.h).
+
+Every op here takes and returns fp32 CUDA tensors whose MEMORY is NHWC (shape (N, H, W, C),
+contiguous); networks.py converts at the network edges so callers keep seeing NCHW, exactly as
+with the reference's nn.Modules.  PyTorch is used for device memory (caching allocator), streams
+and the autograd graph only -- all arithmetic is in the .so; there is no CPU / ATen fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+_precision = L.FP32
+_weights_epoch = 0
+
+
+def set_precision(name):
+    """'fp32' (CUDA-core strict parity) | 'tf32' | 'bf16' (tcgen05 tensor-core paths)."""
+    global _precision
+    _precision = L.PRECISION[name]
+
+
+def get_precision():
+    return {v: k for k, v in L.PRECISION.items()}[_precision]
+
+
+def bump_weights_epoch():
+    """Invalidate every packed-weight cache (called by the fused optimiser, load_state_dict, weights_init
+    and graph replays -- anything that changes parameter memory behind autograd's back)."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("supervised-gan_b200: %s must be a CUDA tensor (the kernels have no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("supervised-gan_b200: %s must be float32, got %s" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------ conv
+class ConvCfg:
+    """Static description of one conv layer + its packed-weight cache."""
+
+    def __init__(self, transposed, k, stride, pad):
+        self.transposed, self.k, self.stride, self.pad = int(transposed), k, stride, pad
+        self._packed = {}
+
+    def desc(self, x_shape, weight):
+        N, H, W, C = x_shape
+        if self.transposed:
+            cin, cout = weight.shape[0], weight.shape[1]
+            Ho = (H - 1) * self.stride - 2 * self.pad + self.k
+            Wo = (W - 1) * self.stride - 2 * self.pad + self.k
+        else:
+            cout, cin = weight.shape[0], weight.shape[1]
+            Ho = (H + 2 * self.pad - self.k) // self.stride + 1
+            Wo = (W + 2 * self.pad - self.k) // self.stride + 1
+        if C != cin:
+            raise RuntimeError("conv: input has %d channels, weight expects %d" % (C, cin))
+        return L.SgkConvDesc(N, cin, H, W, cout, Ho, Wo, self.k, self.stride, self.pad, self.transposed, _precision)
+
+    def packed(self, weight, desc, op):
+        lib = L.load()
+        tag = (weight._version, _weights_epoch, weight.data_ptr(), _precision)
+        ent = self._packed.get(op)
+        if ent is not None and ent[0] == tag:
+            return ent[1]
+        n = lib.sgk_conv_packed_weight_elems(ctypes.byref(desc), op)
+        buf = ent[1] if (ent is not None and ent[1].numel() == n and ent[1].device == weight.device) else \
+            torch.empty(n, dtype=torch.float32, device=weight.device)
+        L.check(lib.sgk_conv_pack_weight(ctypes.byref(desc), op, _p(weight), _p(buf), _stream()), "conv_pack_weight")
+        self._packed[op] = (tag, buf)
+        return buf
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, cfg, act, slope, bias_grad_zero):
+        lib = L.load()
+        x = _chk(x, "conv input")
+        w = _chk(weight.detach(), "conv weight")
+        b = _chk(bias.detach(), "conv bias") if bias is not None else None
+        desc = cfg.desc(x.shape, w)
+        y = torch.empty((desc.N, desc.Hout, desc.Wout, desc.Cout), dtype=torch.float32, device=x.device)
+        wp = cfg.packed(weight, desc, L.OP_FWD)
+        L.check(lib.sgk_conv_fwd(ctypes.byref(desc), _p(x), _p(wp), _p(b), _p(y), act, slope, _stream()), "conv_fwd")
+        ctx.cfg, ctx.desc, ctx.has_bias = cfg, desc, bias is not None
+        # a conv bias that feeds an Instance/BatchNorm has an exactly-zero gradient (the norm removes the mean);
+        # we emit exact zeros instead of the reference's ~1e-9 rounding noise (DESIGN.md "deviations")
+        ctx.act, ctx.slope, ctx.bias_grad_zero = act, slope, bias_grad_zero
+        ctx.weight_ref = weight
+        ctx.save_for_backward(x, y if act != L.ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        cfg, desc = ctx.cfg, ctx.desc
+        x, y = ctx.saved_tensors
+        weight = ctx.weight_ref
+        dy = _chk(dy, "conv grad")
+        st = _stream()
+        if ctx.act != L.ACT_NONE:
+            dpre = torch.empty_like(dy)
+            L.check(lib.sgk_act_bwd(_p(dy), _p(y), _p(dpre), dy.numel(), ctx.act, ctx.slope, st), "act_bwd")
+            dy = dpre
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            wp = cfg.packed(weight, desc, L.OP_DGRAD)
+            L.check(lib.sgk_conv_dgrad(ctypes.byref(desc), _p(dy), _p(wp), _p(gx), st), "conv_dgrad")
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if want_b and ctx.bias_grad_zero:
+            gb = torch.zeros(desc.Cout, dtype=torch.float32, device=dy.device)
+            want_b = False
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty_like(weight)
+            if want_b:
+                gb = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device)
+            nbytes = lib.sgk_conv_wgrad_workspace_bytes(ctypes.byref(desc))
+            ws = _ws(nbytes, dy.device)
+            L.check(lib.sgk_conv_wgrad(ctypes.byref(desc), _p(x), _p(dy), _p(gw), _p(gb) if want_b else None, _p(ws),
+                                       ws.numel(), st), "conv_wgrad")
+        elif want_b:
+            gb = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device)
+            rows = dy.numel() // desc.Cout
+            ws = _ws(lib.sgk_bias_grad_workspace_bytes(rows, desc.Cout), dy.device)
+            L.check(lib.sgk_bias_grad(_p(dy), _p(gb), rows, desc.Cout, _p(ws), ws.numel(), st), "bias_grad")
+        return gx, gw, gb, None, None, None, None
+
+
+def conv(x, weight, bias, cfg, act="none", slope=0.2, bias_grad_zero=False):
+    return _ConvFn.apply(x, weight, bias, cfg, L.ACT[act], float(slope), bool(bias_grad_zero))
+
+
+# ------------------------------------------------------------------------------------------ norm + act
+class _NormActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, per_sample, act, slope, momentum, eps):
+        lib = L.load()
+        x = _chk(x, "norm input")
+        N, H, W, C = x.shape
+        g = _chk(gamma.detach(), "gamma") if gamma is not None else None
+        b = _chk(beta.detach(), "beta") if beta is not None else None
+        groups = N if per_sample else 1
+        y = torch.empty_like(x)
+        stats = torch.empty(groups * C * 2, dtype=torch.float32, device=x.device)
+        ws = _ws(lib.sgk_norm_workspace_bytes(N, C, H, W), x.device)
+        L.check(lib.sgk_norm_act_fwd(_p(x), _p(y), _p(stats), _p(g), _p(b), _p(running_mean), _p(running_var), momentum, eps,
+                                     N, C, H, W, int(per_sample), act, slope, _p(ws), ws.numel(), _stream()), "norm_act_fwd")
+        ctx.args = (per_sample, act, slope, gamma is not None)
+        ctx.save_for_backward(x, stats, g, b)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        per_sample, act, slope, affine = ctx.args
+        x, stats, g, b = ctx.saved_tensors
+        dy = _chk(dy, "norm grad")
+        N, H, W, C = x.shape
+        dx = torch.empty_like(x)
+        dg = torch.empty(C, dtype=torch.float32, device=x.device) if affine else None
+        db = torch.empty(C, dtype=torch.float32, device=x.device) if affine else None
+        ws = _ws(lib.sgk_norm_workspace_bytes(N, C, H, W), x.device)
+        L.check(lib.sgk_norm_act_bwd(_p(dy), _p(x), _p(stats), _p(g), _p(b), _p(dx), _p(dg), _p(db), N, C, H, W,
+                                     int(per_sample), act, slope, _p(ws), ws.numel(), _stream()), "norm_act_bwd")
+        return dx, dg, db, None, None, None, None, None, None, None
+
+
+def instance_norm_act(x, act="none", slope=0.2, eps=1e-5):
+    return _NormActFn.apply(x, None, None, None, None, True, L.ACT[act], float(slope), 0.0, eps)
+
+
+def batch_norm_act(x, gamma, beta, running_mean, running_var, act="none", slope=0.2, momentum=0.1, eps=1e-5):
+    return _NormActFn.apply(x, gamma, beta, running_mean, running_var, False, L.ACT[act], float(slope), momentum, eps)
+
+
+# ------------------------------------------------------------------------------------------ layout
+class _ToNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x, "input")
+        N, C, H, W = x.shape
+        y = torch.empty((N, H, W, C), dtype=torch.float32, device=x.device)
+        L.check(L.load().sgk_layout_nchw_to_nhwc(_p(x), _p(y), N, C, H, W, _stream()), "nchw_to_nhwc")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _chk(dy, "grad")
+        N, H, W, C = dy.shape
+        dx = torch.empty((N, C, H, W), dtype=torch.float32, device=dy.device)
+        L.check(L.load().sgk_layout_nhwc_to_nchw(_p(dy), _p(dx), N, C, H, W, _stream()), "nhwc_to_nchw")
+        return dx
+
+
+class _ToNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x, "input")
+        N, H, W, C = x.shape
+        y = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+        L.check(L.load().sgk_layout_nhwc_to_nchw(_p(x), _p(y), N, C, H, W, _stream()), "nhwc_to_nchw")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _chk(dy, "grad")
+        N, C, H, W = dy.shape
+        dx = torch.empty((N, H, W, C), dtype=torch.float32, device=dy.device)
+        L.check(L.load().sgk_layout_nchw_to_nhwc(_p(dy), _p(dx), N, C, H, W, _stream()), "nchw_to_nhwc")
+        return dx
+
+
+def to_nhwc(x):
+    if x.dim() == 4 and x.shape[1] == 1:  # C == 1: identical memory
+        return x.reshape(x.shape[0], x.shape[2], x.shape[3], 1)
+    return _ToNHWC.apply(x)
+
+
+def to_nchw(x):
+    if x.dim() == 4 and x.shape[3] == 1:
+        return x.reshape(x.shape[0], 1, x.shape[1], x.shape[2])
+    return _ToNCHW.apply(x)
+
+
+# ------------------------------------------------------------------------------------------ activations / concat
+class _ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act, slope):
+        x = _chk(x, "input")
+        y = torch.empty_like(x)
+        L.check(L.load().sgk_act_fwd(_p(x), _p(y), x.numel(), act, slope, _stream()), "act_fwd")
+        ctx.args = (act, slope)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        act, slope = ctx.args
+        (y,) = ctx.saved_tensors
+        dy = _chk(dy, "grad")
+        dx = torch.empty_like(dy)
+        L.check(L.load().sgk_act_bwd(_p(dy), _p(y), _p(dx), dy.numel(), act, slope, _stream()), "act_bwd")
+        return dx, None, None
+
+
+def activation(x, act, slope=0.2):
+    return _ActFn.apply(x, L.ACT[act], float(slope))
+
+
+class _Concat2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _chk(a, "concat a"), _chk(b, "concat b")
+        if a.shape[:3] != b.shape[:3]:
+            raise RuntimeError("concat: spatial shapes differ %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+        Ca, Cb = a.shape[3], b.shape[3]
+        out = torch.empty(a.shape[:3] + (Ca + Cb,), dtype=torch.float32, device=a.device)
+        L.check(L.load().sgk_concat2_nhwc(_p(a), Ca, _p(b), Cb, _p(out), a.numel() // Ca, _stream()), "concat2")
+        ctx.c = (Ca, Cb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        Ca, Cb = ctx.c
+        dy = _chk(dy, "grad")
+        da = torch.empty(dy.shape[:3] + (Ca,), dtype=torch.float32, device=dy.device) if ctx.needs_input_grad[0] else None
+        db = torch.empty(dy.shape[:3] + (Cb,), dtype=torch.float32, device=dy.device) if ctx.needs_input_grad[1] else None
+        if da is not None or db is not None:
+            L.check(L.load().sgk_split2_nhwc(_p(dy), _p(da), Ca, _p(db), Cb, dy.numel() // (Ca + Cb), _stream()), "split2")
+        return da, db
+
+
+def concat_channels(a, b):
+    return _Concat2.apply(a, b)
+
+
+class _Axpy(torch.autograd.Function):
+    """out = a + alpha * b, gradient to a only (b is injected noise)."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha):
+        a, b = _chk(a), _chk(b)
+        out = torch.empty_like(a)
+        L.check(L.load().sgk_axpy(_p(a), _p(b), alpha, _p(out), a.numel(), _stream()), "axpy")
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, None, None
+
+
+def add_noise(a, noise, sigma):
+    return _Axpy.apply(a, noise, float(sigma))
+
+
+class _MulMask(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask):
+        x, mask = _chk(x), _chk(mask)
+        out = torch.empty_like(x)
+        L.check(L.load().sgk_mul(_p(x), _p(mask), _p(out), x.numel(), _stream()), "mul")
+        ctx.save_for_backward(mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        dy = _chk(dy)
+        dx = torch.empty_like(dy)
+        L.check(L.load().sgk_mul(_p(dy), _p(mask), _p(dx), dy.numel(), _stream()), "mul")
+        return dx, None
+
+
+def mul_mask(x, mask):
+    return _MulMask.apply(x, mask)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _chk(a), _chk(b)
+        out = torch.empty_like(a)
+        L.check(L.load().sgk_axpy(_p(a), _p(b), 1.0, _p(out), a.numel(), _stream()), "axpy")
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add_residual(a, b):
+    return _Add.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------ resampling
+class _GaussDecimate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, taps, k, scale):
+        x, taps = _chk(x, "input"), _chk(taps, "taps")
+        N, H, W, C = x.shape
+        Ho, Wo = (H + scale - 1) // scale, (W + scale - 1) // scale
+        y = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=x.device)
+        L.check(L.load().sgk_gauss_decimate_fwd(_p(x), _p(taps), _p(y), N, C, H, W, k, scale, _stream()), "gauss_fwd")
+        ctx.args = (x.shape, k, scale)
+        ctx.save_for_backward(taps)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, k, scale = ctx.args
+        (taps,) = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        dy = _chk(dy, "grad")
+        N, H, W, C = shape
+        dx = torch.empty(shape, dtype=torch.float32, device=dy.device)
+        L.check(L.load().sgk_gauss_decimate_bwd(_p(dy), _p(taps), _p(dx), N, C, H, W, k, scale, _stream()), "gauss_bwd")
+        return dx, None, None, None
+
+
+def gauss_decimate(x, taps, k, scale):
+    return _GaussDecimate.apply(x, taps, k, scale)
+
+
+class _BilinearUp2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x, "input")
+        N, H, W, C = x.shape
+        y = torch.empty((N, 2 * H, 2 * W, C), dtype=torch.float32, device=x.device)
+        L.check(L.load().sgk_bilinear_up2_fwd(_p(x), _p(y), N, C, H, W, _stream()), "bilinear_fwd")
+        ctx.shape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _chk(dy, "grad")
+        N, H, W, C = ctx.shape
+        dx = torch.empty(ctx.shape, dtype=torch.float32, device=dy.device)
+        L.check(L.load().sgk_bilinear_up2_bwd(_p(dy), _p(dx), N, C, H, W, _stream()), "bilinear_bwd")
+        return dx
+
+
+def bilinear_up2(x):
+    return _BilinearUp2.apply(x)
+
+
+class _AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k):
+        x = _chk(x, "input")
+        N, H, W, C = x.shape
+        y = torch.empty((N, H // k, W // k, C), dtype=torch.float32, device=x.device)
+        L.check(L.load().sgk_avgpool_fwd(_p(x), _p(y), N, C, H, W, k, _stream()), "avgpool_fwd")
+        ctx.args = (x.shape, k)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, k = ctx.args
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        dy = _chk(dy, "grad")
+        N, H, W, C = shape
+        dx = torch.empty(shape, dtype=torch.float32, device=dy.device)
+        L.check(L.load().sgk_avgpool_bwd(_p(dy), _p(dx), N, C, H, W, k, _stream()), "avgpool_bwd")
+        return dx, None
+
+
+def avgpool(x, k):
+    return _AvgPool.apply(x, k)
+
+
+# ------------------------------------------------------------------------------------------ losses
+class _LossFn(torch.autograd.Function):
+    """kind: 'gan' (mode, target), 'l1' (y, w), 'bce_pair' (t).  Forward computes value and d/dx in one pass."""
+
+    @staticmethod
+    def forward(ctx, x, kind, mode, target, y, w):
+        lib = L.load()
+        x = _chk(x, "loss input")
+        n = x.numel()
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x)
+        ws = _ws(lib.sgk_loss_workspace_bytes(n), x.device)
+        st = _stream()
+        if kind == "gan":
+            L.check(lib.sgk_gan_loss(_p(x), n, mode, target, _p(out), _p(grad), _p(ws), ws.numel(), st), "gan_loss")
+        elif kind == "l1":
+            y = _chk(y.detach(), "l1 target")
+            w = _chk(w.detach(), "l1 weight") if w is not None else None
+            if y.shape != x.shape or (w is not None and w.shape != x.shape):
+                raise RuntimeError("l1 loss: shapes differ")
+            L.check(lib.sgk_l1_loss(_p(x), _p(y), _p(w), n, _p(out), _p(grad), _p(ws), ws.numel(), st), "l1_loss")
+        else:
+            y = _chk(y.detach(), "bce target")
+            if y.shape != x.shape:
+                raise RuntimeError("bce pair loss: shapes differ")
+            L.check(lib.sgk_bce_pair_loss(_p(x), _p(y), n, _p(out), _p(grad), _p(ws), ws.numel(), st), "bce_pair_loss")
+        ctx.kind = kind
+        ctx.save_for_backward(grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        gout = _chk(gout, "loss grad")
+        gx = torch.empty_like(grad)
+        L.check(L.load().sgk_scale_by_dev_scalar(_p(grad), _p(gout), _p(gx), grad.numel(), _stream()), "scale")
+        gy = None
+        if ctx.needs_input_grad[4]:
+            if ctx.kind != "l1":
+                raise RuntimeError("gradient w.r.t. the target of a BCE loss is not supported (the reference detaches it)")
+            gy = torch.empty_like(grad)
+            neg = torch.empty_like(gout)
+            L.check(L.load().sgk_axpy(_p(torch.zeros_like(gout)), _p(gout), -1.0, _p(neg), 1, _stream()), "axpy")
+            L.check(L.load().sgk_scale_by_dev_scalar(_p(grad), _p(neg), _p(gy), grad.numel(), _stream()), "scale")
+        return gx, None, None, None, gy, None
+
+
+def gan_loss(pred, target_value, use_lsgan):
+    return _LossFn.apply(pred, "gan", 1 if use_lsgan else 0, float(target_value), None, None)
+
+
+def l1_loss(x, y, w=None):
+    return _LossFn.apply(x, "l1", 0, 0.0, y, w)
+
+
+def bce_pair_loss(x, t):
+    return _LossFn.apply(x, "bce_pair", 0, 0.0, t, None)
