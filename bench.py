@@ -1,0 +1,318 @@
+"""Benchmark of the supervised-gan hot path: one fcgan G+D training step (FCGANModel.optimize_parameters).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--precision fp32|tf32]
+
+Workload (BASELINE.json configs[3] at N=1 -- the metric "fcgan 512^2 G+D train steps/sec" is quoted on the fcgan
+config; configs[0] is the same nets at batch 1): deconv G (n_layers_G 5, ngf 32, noise 8x8x8) + 3-scale n_layers D
+(ndf 32, scale 1/2/4), instance norm, BCE, 512x512, 2 channels, batch 8 per GPU, synthetic data, random-init weights,
+pool_size 0 (the host-side image pool is a "next" row), n_update_D = n_update_G = 1.
+
+Prints ONE JSON line (contract in the task statement):
+  value      images/s of the whole job, step replayed from a CUDA graph, inputs resident in HBM
+  e2e        same metric through the public API (FCGANModel.set_input + optimize_parameters + loss read-back),
+             with the pinned-host -> device copy of every batch and the device -> host loss read inside the timed region
+  roofline   dominant kernel family, achieved = algorithmic FLOPs / CUDA-event time of its launches (measured live)
+  cpu_baseline  the oracle port of the reference step (oracle/nets.FcganStep, torch CPU) timed on this box's host cores
+`--impl reference` times that CPU oracle port only (the reference itself is pure Python on PyTorch; its arithmetic lives
+in torch, restated in oracle/).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fcgan 512x512 G+D train throughput (steps/s x global batch)"
+UNIT = "images/s"
+FLOP_PER_SAMPLE_STEP = 85.81e9  # useful conv FLOPs per sample-step, SURVEY.md 8(d)
+
+
+def make_opt(batch, gpu):
+    return argparse.Namespace(
+        isTrain=True, gpu_ids=[gpu], checkpoints_dir="/tmp/sgk_ckpt", name="bench", pretrained_model_dir="",
+        which_channel="rg", batchSize=batch, output_nc=2, input_nc=2, fineSize=512, noise_nc=8, noiseSize=8, ngf=32,
+        which_model_netG="fcgan", norm="instance", no_dropout=True, n_layers_G=5, use_residual=False,
+        add_gaussian_noise=False, gaussian_sigma=0.1, upsample_mode="convt", n_layers_CRN_block=1,
+        no_share_label_block_weights=False, no_lsgan=True, scale_factor=[1, 2, 4], lambda_D=[0.5, 0.4, 0.1],
+        n_layers_D=[3, 3, 3], ndf=32, which_model_netD="n_layers", continue_train=False, which_epoch="latest",
+        pool_size=0, lr=2e-4, beta1=0.5, which_direction="A", n_update_D=1, n_update_G=1, no_logD_trick=False,
+        niter_decay=100)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle leg
+def cpu_oracle_throughput(batch, steps, warmup, seed=0):
+    """images/s of the oracle port of the reference step on this box's host cores (all threads torch will use)."""
+    import torch
+    from oracle import nets as ON
+    gen = torch.Generator().manual_seed(seed)
+    sdG = ON.init_fcgan_generator(gen, 8, 2, 32, 5)
+    sdDs = [ON.init_nlayer_discriminator(gen, 2, 32, 3, s) for s in (1, 2, 4)]
+    st = ON.FcganStep(sdG, sdDs, pool_size=0)
+    real = torch.rand(batch, 2, 512, 512, generator=gen) * 2 - 1
+    for _ in range(warmup):
+        st.step(real, torch.randn(batch, 8, 8, 8, generator=gen))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st.step(real, torch.randn(batch, 8, 8, 8, generator=gen))
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    # bound the CPU work to a few minutes: ~0.55 s per sample-step on 8 cores
+    b = max(1, min(args.batch, int(150.0 / (0.6 * max(total, 1)))))
+    ips, s_per_step, threads = cpu_oracle_throughput(b, args.steps, args.warmup)
+    sample = "oracle port of FCGANModel.optimize_parameters, batch %d of the %d-per-GPU workload, %d timed steps" % (b, args.batch, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "fcgan 512x512 G+D step, deconv G ngf32 + 3-scale D ndf32, BCE, batch %d (CPU sample)" % b},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import supervised_gan_b200 as S
+    from supervised_gan_b200.fcgan_model import FCGANModel
+    from supervised_gan_b200 import dist as sdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S.set_precision(args.precision)
+    lib = S._lib.load()
+    B = args.batch
+    torch.manual_seed(1234 + rank)
+
+    opt = make_opt(B, local)
+    opt.grad_scale = 1.0 / world
+    m = FCGANModel()
+    m.initialize(opt)
+    if world > 1:
+        sdist.broadcast_parameters(list(m.netG.parameters()) + list(m.netG.buffers()) +
+                                   [p for d in m.netD for p in d.parameters()])
+        m.grad_sync = sdist.GradSync(world)
+
+    gen = torch.Generator().manual_seed(99 + rank)
+    host_batches = [(torch.rand(B, 3, 512, 512, generator=gen) * 2 - 1).pin_memory() for _ in range(2)]
+    static_real = torch.empty(B, 2, 512, 512, device=dev)
+    static_real.copy_(host_batches[0][:, :2])
+    m.input = static_real
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- warm-up (eager) + graph capture of the whole step
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(max(3, args.warmup)):
+            m.optimize_parameters()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = None
+    launches_per_step = None
+    if not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            n0 = lib.sgk_launch_count()
+            with torch.cuda.graph(graph):
+                m.optimize_parameters()
+            launches_per_step = lib.sgk_launch_count() - n0
+        except Exception as e:  # capture not possible (e.g. a collective that cannot be captured): stay eager
+            sys.stderr.write("[bench] CUDA graph capture failed (%s); timing the eager step\n" % (e,))
+            graph = None
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+            S.ops.bump_weights_epoch()
+        else:
+            m.optimize_parameters()
+
+    for _ in range(args.warmup):
+        step()
+    # ---------------- timed region 1: device-resident inputs
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = lib.sgk_launch_count()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    eager_launches = lib.sgk_launch_count() - n0
+    clk = clocks.stop()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    gpu_launches = launches_per_step * args.steps if graph is not None else eager_launches
+
+    # ---------------- timed region 2: end to end through the public API (eager), H2D + D2H inside
+    for i in range(2):
+        m.set_input({"A": host_batches[i % 2], "A_paths": ["synthetic"]})
+        m.optimize_parameters()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = args.steps
+    e0.record()
+    sink = 0.0
+    for i in range(e2e_steps):
+        m.set_input({"A": host_batches[i % 2], "A_paths": ["synthetic"]})      # pinned host -> device
+        m.optimize_parameters()
+        errs = m.get_current_errors()                                           # device -> host (3 losses)
+        sink += errs["G_GAN"]
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te)
+    h2d = B * 2 * 512 * 512 * 4
+    d2h = 3 * 4
+
+    # ---------------- roofline leg: per-launch CUDA events on the conv kernels over timed eager steps
+    roof = None
+    cpu = None
+    if rank == 0:
+        timer = S.ops.KernelTimer()
+        S.ops.set_kernel_timer(timer)
+        for _ in range(2):
+            m.optimize_parameters()
+        summ = timer.summary()
+        S.ops.set_kernel_timer(None)
+        fam = {}
+        for tag, e in summ.items():
+            f = fam.setdefault(tag.split(" ")[0], {"ms": 0.0, "flops": 0.0, "launches": 0})
+            f["ms"] += e["ms"]; f["flops"] += e["flops"]; f["launches"] += e["launches"]
+        top_tag, top = max(summ.items(), key=lambda kv: kv[1]["ms"])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
+        conv_ms = sum(f["ms"] for f in fam.values()) / 2.0
+        roof = {"bound": "tensor", "kernel": top_tag, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
+                "conv_families": {k: {"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "ms_per_step": v["ms"] / 2.0,
+                                      "launches_per_step": v["launches"] // 2} for k, v in fam.items()},
+                "conv_ms_per_step_eager": conv_ms,
+                "step_tensor_frac": (B * world * args.steps / (ms * 1e-3)) * FLOP_PER_SAMPLE_STEP / 1e12 / peak / world}
+        if not args.no_cpu_baseline:
+            ips, s_per_step, threads = cpu_oracle_throughput(B, 3, 1)
+            cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "oracle port of the reference step (torch CPU), the same batch-%d workload, 1 warm-up + 3 timed steps, %.2f s/step" % (B, s_per_step)}
+
+    if rank == 0:
+        ips = B * world * args.steps / (ms * 1e-3)
+        line = {"metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "steps_per_sec": args.steps / (ms * 1e-3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
+                "config": {"workload": "fcgan 512x512 G+D step (BASELINE configs[3]): deconv G n_layers 5 ngf 32 noise 8x8x8 + "
+                                       "3-scale n_layers D ndf 32 scale 1/2/4, instance norm, BCE, 2 channels, pool_size 0",
+                           "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "cuda_graph": graph is not None,
+                           "l2": "inputs larger than L2: the step streams > 1 GB of activations per replay (126 MB L2), no flush"},
+                "clocks": clk, "gpu_launches": int(gpu_launches),
+                "e2e": {"value": B * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "api": "FCGANModel.set_input + optimize_parameters + get_current_errors (eager)"},
+                "roofline": roof, "cpu_baseline": cpu, "loss_G_checksum": sink / max(e2e_steps, 1)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU")
+    ap.add_argument("--precision", default=os.environ.get("SGK_PRECISION", "fp32"))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

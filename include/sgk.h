@@ -74,6 +74,8 @@ typedef struct SgkConvDesc {
 
 int sgk_version(void);
 const char* sgk_last_error(void);
+/* total kernels this library has launched (or captured into a graph) in this process so far */
+long long sgk_launch_count(void);
 /* number of SMs / compute capability of the current device (sanity check by the host side) */
 int sgk_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -31,6 +31,7 @@ P = c_void_p
 SIGNATURES = {
     "sgk_version": (c_int, []),
     "sgk_last_error": (c_char_p, []),
+    "sgk_launch_count": (ctypes.c_longlong, []),
     "sgk_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "sgk_conv_packed_weight_elems": (c_size_t, [POINTER(SgkConvDesc), c_int]),
     "sgk_conv_pack_weight": (c_int, [POINTER(SgkConvDesc), c_int, P, P, P]),

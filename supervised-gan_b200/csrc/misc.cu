@@ -1,7 +1,7 @@
 // Library plumbing (errors, device info) and the small bandwidth-bound helpers:
 // layout conversion at the network edges, standalone activations, bias gradient, NHWC concat/split.
 #include "common.cuh"
-#include <mutex>
+#include <atomic>
 
 namespace sgk {
 
@@ -18,6 +18,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
   return SGK_ECUDA;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached[64] = {0};
@@ -167,6 +170,7 @@ static unsigned ew_blocks(size_t work_items) {
 using namespace sgk;
 
 extern "C" int sgk_version(void) { return SGK_VERSION; }
+extern "C" long long sgk_launch_count(void) { return sgk::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* sgk_last_error(void) { return sgk::g_err; }
 extern "C" int sgk_device_info(int* sm, int* major, int* minor) {
   int dev = 0;

@@ -9,8 +9,28 @@
 
 namespace sgk {
 
+template <int V>
+__device__ __forceinline__ void vload(const float* p, float (&v)[V]) {
+  if constexpr (V == 4) {
+    float4 t = ld_stream(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = __ldg(p + i);
+  }
+}
+template <int V>
+__device__ __forceinline__ void vstore(float* p, const float (&v)[V]) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) p[i] = v[i];
+  }
+}
+
 struct NormGeom {
-  int C, C4;               // channels, float4 columns
+  int C, C4;               // channels, vector columns (C/4 when C % 4 == 0, else C)
   int cols;                // float4 columns handled by one block (<= 64)
   int rlanes;              // 256 / cols row lanes
   long long rows;          // rows per group
@@ -21,7 +41,8 @@ struct NormGeom {
 
 static NormGeom norm_geom(int N, int C, int H, int W, int per_sample) {
   NormGeom g;
-  g.C = C; g.C4 = C / 4;
+  const int V = (C & 3) ? 1 : 4;
+  g.C = C; g.C4 = C / V;
   g.cols = g.C4 < 64 ? g.C4 : 64;
   while (256 % g.cols) --g.cols;  // C4 is a multiple of cols only when it divides; handled by col-groups + guard
   g.rlanes = 256 / g.cols;
@@ -42,59 +63,69 @@ static NormGeom norm_geom(int N, int C, int H, int W, int per_sample) {
 
 // ------------------------------------------------------------------------------ forward stats
 // partial layout: part[((group*chunks + chunk)*C + c)*2 + {0,1}]
+template <int V>
 __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ x, float* __restrict__ part, int C,
                                                          int cols, int rlanes, long long rows, int chunks,
                                                          long long rows_per_chunk) {
-  extern __shared__ float sm[];  // [rlanes][cols*4][2]
-  const int C4 = C >> 2;
+  extern __shared__ float sm[];  // [rlanes][cols][2*V]
+  const int CV = C / V;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
-  const int c4 = blockIdx.y * cols + tc;
+  const int cv = blockIdx.y * cols + tc;
   const int group = blockIdx.z, chunk = blockIdx.x;
-  const float4* __restrict__ xg = reinterpret_cast<const float4*>(x) + (long long)group * rows * C4;
-  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  if (c4 < C4) {
-    const float4 K = __ldg(xg + c4);
+  const float* __restrict__ xg = x + (long long)group * rows * C;
+  float s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  if (cv < CV) {
+    float K[V];
+    vload<V>(xg + cv * V, K);
     long long r0 = (long long)chunk * rows_per_chunk;
     long long r1 = r0 + rows_per_chunk;
     if (r1 > rows) r1 = rows;
     long long r = r0 + tr;
     // 4 independent loads in flight per thread
     for (; r + 3LL * rlanes < r1; r += 4LL * rlanes) {
-      float4 v[4];
+      float v[4][V];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ld_stream(xg + (r + (long long)u * rlanes) * C4 + c4);
+      for (int u = 0; u < 4; ++u) vload<V>(xg + (r + (long long)u * rlanes) * C + cv * V, v[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float a = v[u].x - K.x, b = v[u].y - K.y, c = v[u].z - K.z, d = v[u].w - K.w;
-        s1.x += a; s1.y += b; s1.z += c; s1.w += d;
-        s2.x = fmaf(a, a, s2.x); s2.y = fmaf(b, b, s2.y); s2.z = fmaf(c, c, s2.z); s2.w = fmaf(d, d, s2.w);
-      }
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float a = v[u][i] - K[i];
+          s1[i] += a;
+          s2[i] = fmaf(a, a, s2[i]);
+        }
     }
     for (; r < r1; r += rlanes) {
-      float4 v = ld_stream(xg + r * C4 + c4);
-      float a = v.x - K.x, b = v.y - K.y, c = v.z - K.z, d = v.w - K.w;
-      s1.x += a; s1.y += b; s1.z += c; s1.w += d;
-      s2.x = fmaf(a, a, s2.x); s2.y = fmaf(b, b, s2.y); s2.z = fmaf(c, c, s2.z); s2.w = fmaf(d, d, s2.w);
+      float v[V];
+      vload<V>(xg + r * C + cv * V, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float a = v[i] - K[i];
+        s1[i] += a;
+        s2[i] = fmaf(a, a, s2[i]);
+      }
     }
   }
-  float* my = sm + ((long long)tr * cols + tc) * 8;
-  my[0] = s1.x; my[1] = s1.y; my[2] = s1.z; my[3] = s1.w;
-  my[4] = s2.x; my[5] = s2.y; my[6] = s2.z; my[7] = s2.w;
+  float* my = sm + ((long long)tr * cols + tc) * 2 * V;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { my[i] = s1[i]; my[V + i] = s2[i]; }
   __syncthreads();
-  if (tr == 0 && c4 < C4) {
-    float acc[8];
+  if (tr == 0 && cv < CV) {
+    float acc[2 * V];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 2 * V; ++i) acc[i] = 0.f;
     for (int l = 0; l < rlanes; ++l) {
-      const float* o = sm + ((long long)l * cols + tc) * 8;
+      const float* o = sm + ((long long)l * cols + tc) * 2 * V;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += o[i];
+      for (int i = 0; i < 2 * V; ++i) acc[i] += o[i];
     }
-    float* dst = part + (((long long)group * chunks + chunk) * C + c4 * 4) * 2;
+    float* dst = part + (((long long)group * chunks + chunk) * C + cv * V) * 2;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < V; ++i) {
       dst[i * 2 + 0] = acc[i];
-      dst[i * 2 + 1] = acc[4 + i];
+      dst[i * 2 + 1] = acc[V + i];
     }
   }
 }
@@ -126,30 +157,27 @@ __global__ void norm_finalize_kernel(const float* __restrict__ x, const float* _
 }
 
 // ------------------------------------------------------------------------------ forward apply
+template <int V>
 __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                          const float* __restrict__ stats, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, int C, long long rows_per_group,
-                                                         long long total4, int act, float slope) {
-  const int C4 = C >> 2;
-  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
-  float4* __restrict__ y4 = reinterpret_cast<float4*>(y);
+                                                         long long totalv, int act, float slope) {
+  const int CV = C / V;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
-    long long row = i / C4;
-    int c = (int)(i - row * C4) * 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += stride) {
+    long long row = i / CV;
+    int c = (int)(i - row * CV) * V;
     int group = (int)(row / rows_per_group);
-    float4 v = ld_stream(x4 + i);
-    const float4* st = reinterpret_cast<const float4*>(stats + ((long long)group * C + c) * 2);
-    float4 s01 = __ldg(st), s23 = __ldg(st + 1);  // (mean0, rstd0, mean1, rstd1), (mean2, rstd2, mean3, rstd3)
-    float r[4] = {(v.x - s01.x) * s01.y, (v.y - s01.z) * s01.w, (v.z - s23.x) * s23.y, (v.w - s23.z) * s23.w};
-    if (gamma != nullptr) {
-      float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-      r[0] = fmaf(r[0], g.x, b.x); r[1] = fmaf(r[1], g.y, b.y); r[2] = fmaf(r[2], g.z, b.z); r[3] = fmaf(r[3], g.w, b.w);
+    float v[V], r[V];
+    vload<V>(x + i * V, v);
+    const float* st = stats + ((long long)group * C + c) * 2;  // (mean, rstd) pairs
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float t = (v[k] - __ldg(st + 2 * k)) * __ldg(st + 2 * k + 1);
+      if (gamma != nullptr) t = fmaf(t, __ldg(gamma + c + k), __ldg(beta + c + k));
+      r[k] = act_apply(t, act, slope);
     }
-    float4 o = make_float4(act_apply(r[0], act, slope), act_apply(r[1], act, slope), act_apply(r[2], act, slope),
-                           act_apply(r[3], act, slope));
-    y4[i] = o;
+    vstore<V>(y + i * V, r);
   }
 }
 
@@ -161,6 +189,7 @@ __device__ __forceinline__ float act_grad_pre(float z, int act, float slope) {
   return 1.f;
 }
 
+template <int V>
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                               const float* __restrict__ stats,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -168,76 +197,76 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
                                                               long long rows, int chunks, long long rows_per_chunk, int act,
                                                               float slope) {
   extern __shared__ float sm[];
-  const int C4 = C >> 2;
+  const int CV = C / V;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
-  const int c4 = blockIdx.y * cols + tc;
+  const int cv = blockIdx.y * cols + tc;
   const int group = blockIdx.z, chunk = blockIdx.x;
-  const float4* __restrict__ xg = reinterpret_cast<const float4*>(x) + (long long)group * rows * C4;
-  const float4* __restrict__ dg = reinterpret_cast<const float4*>(dy) + (long long)group * rows * C4;
-  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c4 < C4) {
-    float mean[4], rstd[4], ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* __restrict__ xg = x + (long long)group * rows * C;
+  const float* __restrict__ dg = dy + (long long)group * rows * C;
+  float s1[V], s2[V];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      mean[i] = __ldg(stats + ((long long)group * C + c4 * 4 + i) * 2);
-      rstd[i] = __ldg(stats + ((long long)group * C + c4 * 4 + i) * 2 + 1);
-      if (gamma != nullptr) { ga[i] = __ldg(gamma + c4 * 4 + i); be[i] = __ldg(beta + c4 * 4 + i); }
+  for (int i = 0; i < V; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  if (cv < CV) {
+    float mean[V], rstd[V], ga[V], be[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      mean[i] = __ldg(stats + ((long long)group * C + cv * V + i) * 2);
+      rstd[i] = __ldg(stats + ((long long)group * C + cv * V + i) * 2 + 1);
+      ga[i] = gamma != nullptr ? __ldg(gamma + cv * V + i) : 1.f;
+      be[i] = gamma != nullptr ? __ldg(beta + cv * V + i) : 0.f;
     }
     long long r0 = (long long)chunk * rows_per_chunk;
     long long r1 = r0 + rows_per_chunk;
     if (r1 > rows) r1 = rows;
     long long r = r0 + tr;
     for (; r + (long long)rlanes < r1; r += 2LL * rlanes) {
-      float4 xv[2], dv[2];
+      float xv[2][V], dv[2][V];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        xv[u] = ld_stream(xg + (r + (long long)u * rlanes) * C4 + c4);
-        dv[u] = ld_stream(dg + (r + (long long)u * rlanes) * C4 + c4);
+        vload<V>(xg + (r + (long long)u * rlanes) * C + cv * V, xv[u]);
+        vload<V>(dg + (r + (long long)u * rlanes) * C + cv * V, dv[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-        const float ds[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float xh = (xs[i] - mean[i]) * rstd[i];
-          float g = ds[i] * act_grad_pre(fmaf(xh, ga[i], be[i]), act, slope);
+        for (int i = 0; i < V; ++i) {
+          float xh = (xv[u][i] - mean[i]) * rstd[i];
+          float g = dv[u][i] * act_grad_pre(fmaf(xh, ga[i], be[i]), act, slope);
           s1[i] += g;
           s2[i] = fmaf(g, xh, s2[i]);
         }
-      }
     }
     for (; r < r1; r += rlanes) {
-      float4 xv = ld_stream(xg + r * C4 + c4), dv = ld_stream(dg + r * C4 + c4);
-      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-      const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+      float xv[V], dv[V];
+      vload<V>(xg + r * C + cv * V, xv);
+      vload<V>(dg + r * C + cv * V, dv);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float xh = (xs[i] - mean[i]) * rstd[i];
-        float g = ds[i] * act_grad_pre(fmaf(xh, ga[i], be[i]), act, slope);
+      for (int i = 0; i < V; ++i) {
+        float xh = (xv[i] - mean[i]) * rstd[i];
+        float g = dv[i] * act_grad_pre(fmaf(xh, ga[i], be[i]), act, slope);
         s1[i] += g;
         s2[i] = fmaf(g, xh, s2[i]);
       }
     }
   }
-  float* my = sm + ((long long)tr * cols + tc) * 8;
+  float* my = sm + ((long long)tr * cols + tc) * 2 * V;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { my[i] = s1[i]; my[4 + i] = s2[i]; }
+  for (int i = 0; i < V; ++i) { my[i] = s1[i]; my[V + i] = s2[i]; }
   __syncthreads();
-  if (tr == 0 && c4 < C4) {
-    float acc[8];
+  if (tr == 0 && cv < CV) {
+    float acc[2 * V];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 2 * V; ++i) acc[i] = 0.f;
     for (int l = 0; l < rlanes; ++l) {
-      const float* o = sm + ((long long)l * cols + tc) * 8;
+      const float* o = sm + ((long long)l * cols + tc) * 2 * V;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += o[i];
+      for (int i = 0; i < 2 * V; ++i) acc[i] += o[i];
     }
-    float* dst = part + (((long long)group * chunks + chunk) * C + c4 * 4) * 2;
+    float* dst = part + (((long long)group * chunks + chunk) * C + cv * V) * 2;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < V; ++i) {
       dst[i * 2 + 0] = acc[i];
-      dst[i * 2 + 1] = acc[4 + i];
+      dst[i * 2 + 1] = acc[V + i];
     }
   }
 }
@@ -260,26 +289,23 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, float* 
   sums[idx * 2 + 1] = s2 * inv_n;
 }
 
+template <int V>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                              const float* __restrict__ stats, const float* __restrict__ sums,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              float* __restrict__ dx, int C, long long rows_per_group,
-                                                             long long total4, int act, float slope) {
-  const int C4 = C >> 2;
-  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
-  const float4* __restrict__ d4 = reinterpret_cast<const float4*>(dy);
-  float4* __restrict__ o4 = reinterpret_cast<float4*>(dx);
+                                                             long long totalv, int act, float slope) {
+  const int CV = C / V;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
-    long long row = i / C4;
-    int c = (int)(i - row * C4) * 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += stride) {
+    long long row = i / CV;
+    int c = (int)(i - row * CV) * V;
     int group = (int)(row / rows_per_group);
-    float4 xv = ld_stream(x4 + i), dv = ld_stream(d4 + i);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-    const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
-    float r[4];
+    float xs[V], ds[V], r[V];
+    vload<V>(x + i * V, xs);
+    vload<V>(dy + i * V, ds);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < V; ++k) {
       long long si = ((long long)group * C + c + k) * 2;
       float mean = __ldg(stats + si), rstd = __ldg(stats + si + 1);
       float m1 = __ldg(sums + si), m2 = __ldg(sums + si + 1);
@@ -288,7 +314,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __rest
       float g = ds[k] * act_grad_pre(fmaf(xh, ga, be), act, slope);
       r[k] = ga * rstd * (g - m1 - xh * m2);
     }
-    o4[i] = make_float4(r[0], r[1], r[2], r[3]);
+    vstore<V>(dx + i * V, r);
   }
 }
 
@@ -296,7 +322,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __rest
 using namespace sgk;
 
 extern "C" size_t sgk_norm_workspace_bytes(int N, int C, int H, int W) {
-  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || (C & 3)) return 0;
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
   // worst case over per_sample in {0,1}: partials [groups*chunks*C*2] + sums [groups*C*2]
   size_t best = 0;
   for (int ps = 0; ps < 2; ++ps) {
@@ -310,7 +336,6 @@ extern "C" size_t sgk_norm_workspace_bytes(int N, int C, int H, int W) {
 static int norm_check(const void* a, const void* b, int N, int C, int H, int W, int act) {
   SGK_CHECK_ARG(a && b, "sgk_norm: null argument");
   SGK_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0, "sgk_norm: bad shape");
-  if (C & 3) { set_error("sgk_norm: C=%d must be a multiple of 4", C); return SGK_EUNSUPPORTED; }
   if (act != SGK_ACT_NONE && act != SGK_ACT_RELU && act != SGK_ACT_LRELU) {
     set_error("sgk_norm: activation %d cannot be fused with a norm", act);
     return SGK_EUNSUPPORTED;
@@ -332,8 +357,10 @@ extern "C" int sgk_norm_act_fwd(const float* x, float* y, float* stats, const fl
   if (need > workspace_bytes) { set_error("sgk_norm_act_fwd: workspace %zu < %zu", workspace_bytes, need); return SGK_EWORKSPACE; }
   float* part = (float*)workspace;
   dim3 grid((unsigned)g.chunks, (unsigned)ceil_div(g.C4, g.cols), (unsigned)g.groups);
-  size_t smem = (size_t)g.rlanes * g.cols * 8 * sizeof(float);
-  norm_stats_kernel<<<grid, 256, smem, st>>>(x, part, C, g.cols, g.rlanes, g.rows, g.chunks, g.rows_per_chunk);
+  const bool vec = (C & 3) == 0;
+  size_t smem = (size_t)g.rlanes * g.cols * (vec ? 8 : 2) * sizeof(float);
+  if (vec) norm_stats_kernel<4><<<grid, 256, smem, st>>>(x, part, C, g.cols, g.rlanes, g.rows, g.chunks, g.rows_per_chunk);
+  else norm_stats_kernel<1><<<grid, 256, smem, st>>>(x, part, C, g.cols, g.rlanes, g.rows, g.chunks, g.rows_per_chunk);
   SGK_LAUNCH_CHECK("norm_stats_kernel");
   int gc = g.groups * C;
   norm_finalize_kernel<<<ceil_div(gc, 128), 128, 0, st>>>(x, part, stats, running_mean, running_var, momentum, eps, C,
@@ -343,7 +370,8 @@ extern "C" int sgk_norm_act_fwd(const float* x, float* y, float* stats, const fl
   long long blocks = ceil_div64(total4, 256 * 4);
   long long cap = 16LL * sm_count();
   if (blocks > cap) blocks = cap;
-  norm_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, stats, gamma, beta, C, g.rows, total4, act, slope);
+  if (vec) norm_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, y, stats, gamma, beta, C, g.rows, total4, act, slope);
+  else norm_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, y, stats, gamma, beta, C, g.rows, total4, act, slope);
   SGK_LAUNCH_CHECK("norm_apply_kernel");
   return SGK_OK;
 }
@@ -361,9 +389,12 @@ extern "C" int sgk_norm_act_bwd(const float* dy, const float* x, const float* st
   float* part = (float*)workspace;
   float* sums = part + (size_t)g.groups * g.chunks * C * 2;
   dim3 grid((unsigned)g.chunks, (unsigned)ceil_div(g.C4, g.cols), (unsigned)g.groups);
-  size_t smem = (size_t)g.rlanes * g.cols * 8 * sizeof(float);
-  norm_bwd_reduce_kernel<<<grid, 256, smem, st>>>(dy, x, stats, gamma, beta, part, C, g.cols, g.rlanes, g.rows, g.chunks,
-                                                  g.rows_per_chunk, act, slope);
+  const bool vec = (C & 3) == 0;
+  size_t smem = (size_t)g.rlanes * g.cols * (vec ? 8 : 2) * sizeof(float);
+  if (vec) norm_bwd_reduce_kernel<4><<<grid, 256, smem, st>>>(dy, x, stats, gamma, beta, part, C, g.cols, g.rlanes, g.rows,
+                                                             g.chunks, g.rows_per_chunk, act, slope);
+  else norm_bwd_reduce_kernel<1><<<grid, 256, smem, st>>>(dy, x, stats, gamma, beta, part, C, g.cols, g.rlanes, g.rows,
+                                                          g.chunks, g.rows_per_chunk, act, slope);
   SGK_LAUNCH_CHECK("norm_bwd_reduce_kernel");
   int gc = g.groups * C;
   norm_bwd_finalize_kernel<<<ceil_div(gc, 128), 128, 0, st>>>(part, sums, dgamma, dbeta, C, g.rows, g.chunks, g.groups);
@@ -372,7 +403,8 @@ extern "C" int sgk_norm_act_bwd(const float* dy, const float* x, const float* st
   long long blocks = ceil_div64(total4, 256 * 4);
   long long cap = 16LL * sm_count();
   if (blocks > cap) blocks = cap;
-  norm_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(dy, x, stats, sums, gamma, beta, dx, C, g.rows, total4, act, slope);
+  if (vec) norm_bwd_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(dy, x, stats, sums, gamma, beta, dx, C, g.rows, total4, act, slope);
+  else norm_bwd_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(dy, x, stats, sums, gamma, beta, dx, C, g.rows, total4, act, slope);
   SGK_LAUNCH_CHECK("norm_bwd_apply_kernel");
   return SGK_OK;
 }

@@ -304,6 +304,13 @@ def _run_sequence(mods, x, final_act=None):
         m = mods[i]
         nxt = mods[i + 1] if i + 1 < n else None
         if isinstance(m, (Conv2d, ConvTranspose2d)):
+            nxt2 = mods[i + 2] if i + 2 < n else None
+            if isinstance(nxt, Upsample) and isinstance(nxt2, (BatchNorm2d, InstanceNorm2d)):
+                # CRN bilinear block Conv -> Upsample -> Norm (networks.py:751-755): interpolation preserves constants,
+                # so the conv bias still has an exactly-zero gradient
+                x = m.run(x, "none", 0.2, bias_feeds_norm=True)
+                i += 1
+                continue
             if isinstance(nxt, (BatchNorm2d, InstanceNorm2d)):
                 x = m.run(x, "none", 0.2, bias_feeds_norm=True)
                 i += 1

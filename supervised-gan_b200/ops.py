@@ -36,6 +36,55 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing of the conv kernels (bench.py's roofline leg).  Events are recorded on
+    the stream the kernel is launched on; nothing is synchronised until `summary()`."""
+
+    def __init__(self):
+        self.records = []
+
+    def time(self, tag, flops, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn()
+        b.record()
+        self.records.append((tag, flops, a, b))
+        return rc
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, flops, a, b in self.records:
+            e = out.setdefault(tag, {"launches": 0, "ms": 0.0, "flops": 0.0})
+            e["launches"] += 1
+            e["ms"] += a.elapsed_time(b)
+            e["flops"] += flops
+        return out
+
+
+_timer = None
+
+
+def set_kernel_timer(t):
+    global _timer
+    _timer = t
+
+
+def _timed(tag, flops, fn):
+    return fn() if _timer is None else _timer.time(tag, flops, fn)
+
+
+def _conv_tag(op, d):
+    return "%s %s %d->%d k%ds%dp%d %dx%d N%d" % (op, "convT" if d.transposed else "conv", d.Cin, d.Cout, d.k, d.stride,
+                                                  d.pad, d.Hin, d.Win, d.N)
+
+
+def _conv_flops(d):
+    if d.transposed:
+        return 2.0 * d.N * d.Hin * d.Win * d.Cin * d.Cout * d.k * d.k
+    return 2.0 * d.N * d.Hout * d.Wout * d.Cin * d.Cout * d.k * d.k
+
+
 def _chk(t, name="tensor"):
     if t is None:
         return None
@@ -100,7 +149,8 @@ class _ConvFn(torch.autograd.Function):
         desc = cfg.desc(x.shape, w)
         y = torch.empty((desc.N, desc.Hout, desc.Wout, desc.Cout), dtype=torch.float32, device=x.device)
         wp = cfg.packed(weight, desc, L.OP_FWD)
-        L.check(lib.sgk_conv_fwd(ctypes.byref(desc), _p(x), _p(wp), _p(b), _p(y), act, slope, _stream()), "conv_fwd")
+        L.check(_timed(_conv_tag("fwd", desc), _conv_flops(desc), lambda: lib.sgk_conv_fwd(
+            ctypes.byref(desc), _p(x), _p(wp), _p(b), _p(y), act, slope, _stream())), "conv_fwd")
         ctx.cfg, ctx.desc, ctx.has_bias = cfg, desc, bias is not None
         # a conv bias that feeds an Instance/BatchNorm has an exactly-zero gradient (the norm removes the mean);
         # we emit exact zeros instead of the reference's ~1e-9 rounding noise (DESIGN.md "deviations")
@@ -125,7 +175,8 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             wp = cfg.packed(weight, desc, L.OP_DGRAD)
-            L.check(lib.sgk_conv_dgrad(ctypes.byref(desc), _p(dy), _p(wp), _p(gx), st), "conv_dgrad")
+            L.check(_timed(_conv_tag("dgrad", desc), _conv_flops(desc), lambda: lib.sgk_conv_dgrad(
+                ctypes.byref(desc), _p(dy), _p(wp), _p(gx), st)), "conv_dgrad")
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if want_b and ctx.bias_grad_zero:
             gb = torch.zeros(desc.Cout, dtype=torch.float32, device=dy.device)
@@ -136,8 +187,8 @@ class _ConvFn(torch.autograd.Function):
                 gb = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device)
             nbytes = lib.sgk_conv_wgrad_workspace_bytes(ctypes.byref(desc))
             ws = _ws(nbytes, dy.device)
-            L.check(lib.sgk_conv_wgrad(ctypes.byref(desc), _p(x), _p(dy), _p(gw), _p(gb) if want_b else None, _p(ws),
-                                       ws.numel(), st), "conv_wgrad")
+            L.check(_timed(_conv_tag("wgrad", desc), _conv_flops(desc), lambda: lib.sgk_conv_wgrad(
+                ctypes.byref(desc), _p(x), _p(dy), _p(gw), _p(gb) if want_b else None, _p(ws), ws.numel(), st)), "conv_wgrad")
         elif want_b:
             gb = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device)
             rows = dy.numel() // desc.Cout

@@ -31,3 +31,24 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"))
     return load
+
+
+# ---------------------------------------------------------------------------------------------
+# Robust gradient comparison.  Every fp32 implementation (the reference's included) flips the side
+# of a LeakyReLU/ReLU kink for the handful of elements whose normalised pre-activation is within
+# rounding error of 0 (|xhat| < ~3e-6, about 2 per million elements); one flip changes that element's
+# gradient by O(1) and smears ~1e-2 (relative to max) into the gradients upstream of it
+# (tools/debug_d.py shows the event).  Max-norm comparisons are therefore meaningless for whole-network
+# gradients; we bound the bulk (quantile) tightly and the energy of the outliers (relative L2) loosely.
+# ---------------------------------------------------------------------------------------------
+def grad_close(got, ref, what="", q_tol=1e-2, l2_tol=2e-2, frac=0.99):
+    import numpy as np
+    got = np.asarray(got, dtype=np.float64).ravel()
+    ref = np.asarray(ref, dtype=np.float64).ravel()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    scale = max(np.abs(ref).max(), 1e-30)
+    d = np.abs(got - ref) / scale
+    q = np.quantile(d, frac) if d.size > 1 else d.max()
+    l2 = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30)
+    assert q <= q_tol, "%s: %.0f%%-quantile of |err|/max = %.3e > %.1e" % (what, 100 * frac, q, q_tol)
+    assert l2 <= l2_tol, "%s: relative L2 error %.3e > %.1e" % (what, l2, l2_tol)

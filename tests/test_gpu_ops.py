@@ -29,12 +29,18 @@ def nchw(t):  # NHWC cuda tensor -> NCHW numpy fp64
     return np.transpose(t.detach().cpu().double().numpy(), (0, 3, 1, 2))
 
 
-def close(got, ref, tol, what=""):
+def close(got, ref, tol, what="", mask=None):
+    """max |got-ref| / max|ref| <= tol.  `mask` (bool, same shape) drops elements whose pre-activation sits within
+    rounding error of an activation kink, where the derivative is legitimately implementation-defined."""
     ref = np.asarray(ref, dtype=np.float64)
     got = np.asarray(got, dtype=np.float64)
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     scale = max(np.abs(ref).max(), 1e-6)
-    err = np.abs(got - ref).max() / scale
+    d = np.abs(got - ref)
+    if mask is not None:
+        assert mask.mean() > 0.99
+        d = d * mask
+    err = d.max() / scale
     assert err <= tol, "%s: rel-to-max error %.3e > %.1e" % (what, err, tol)
 
 
@@ -102,6 +108,12 @@ def test_conv_fused_activation(S, act):
     xt, wt, bt = nhwc(x).requires_grad_(True), dev(w).requires_grad_(True), dev(b).requires_grad_(True)
     yt = S.ops.conv(xt, wt, bt, cfg, act, 0.2)
     close(nchw(yt), y, 2e-5, "fwd")
+    # keep the kinks out of the comparison: zero the upstream gradient where |pre-activation| < 1e-4
+    keep = np.abs(pre) > 1e-4
+    dy = dy * keep
+    dpre = O.act_bwd(dy, pre, y, act)
+    xt.grad = wt.grad = bt.grad = None
+    yt = S.ops.conv(xt, wt, bt, cfg, act, 0.2)
     yt.backward(nhwc(dy))
     close(nchw(xt.grad), O.conv2d_dgrad(dpre, w, x.shape, 2, 2), 3e-5, "dgrad")
     dw, db = O.conv2d_wgrad(dpre, x, w.shape, 2, 2)
@@ -119,13 +131,13 @@ def test_conv_bias_feeding_norm_gets_exact_zero_grad(S):
 
 
 @pytest.mark.parametrize("shape,act", [((2, 64, 33, 29), "lrelu"), ((1, 256, 9, 9), "lrelu"), ((2, 32, 16, 16), "relu"),
-                                       ((3, 8, 5, 5), "none"), ((1, 96, 12, 12), "lrelu"), ((1, 64, 128, 128), "relu")])
+                                       ((3, 8, 5, 5), "none"), ((1, 96, 12, 12), "lrelu"), ((2, 2, 9, 9), "relu"), ((1, 6, 7, 5), "lrelu"), ((1, 64, 128, 128), "relu")])
 def test_instance_norm_act(S, shape, act):
     rng = np.random.default_rng(1)
     x = rng.standard_normal(shape) * 2 + 3          # non-zero mean: exercises the shifted-sum statistics
     xh, mean, rstd = O.instance_norm_fwd(x)
     y = O.act_fwd(xh, act)
-    dy = rng.standard_normal(shape)
+    dy = rng.standard_normal(shape) * (np.abs(xh) > 1e-4)      # keep activation kinks out of the comparison
     dx = O.instance_norm_bwd(O.act_bwd(dy, xh, y, act), xh, rstd)
     xt = nhwc(x).requires_grad_(True)
     yt = S.ops.instance_norm_act(xt, act, 0.2)
@@ -144,7 +156,7 @@ def test_batch_norm_act(S, shape, act):
     rm0, rv0 = rm.copy(), rv.copy()
     z, xh, rstd = O.batch_norm_fwd(x, g, b, rm, rv)
     y = O.act_fwd(z, act)
-    dy = rng.standard_normal(shape)
+    dy = rng.standard_normal(shape) * (np.abs(z) > 1e-4)       # keep activation kinks out of the comparison
     dx, dg, db = O.batch_norm_bwd(O.act_bwd(dy, z, y, act), xh, rstd, g)
     xt = nhwc(x).requires_grad_(True)
     gt, bt = dev(g).requires_grad_(True), dev(b).requires_grad_(True)
@@ -293,7 +305,7 @@ def test_fused_adam_matches_oracle(S):
 
 def test_errors_are_loud(S):
     with pytest.raises(RuntimeError):
-        S.ops.instance_norm_act(torch.zeros(1, 4, 4, 6, device="cuda"))          # C % 4 != 0
+        S.ops.instance_norm_act(torch.zeros(1, 4, 4, 8, device="cuda"), "tanh")   # tanh cannot be fused with a norm
     with pytest.raises(RuntimeError):
         S.ops.conv(torch.zeros(1, 4, 4, 3), torch.zeros(4, 3, 3, 3), None, S.ops.ConvCfg(False, 3, 1, 1))  # CPU tensor
     with pytest.raises(RuntimeError):
