@@ -554,7 +554,7 @@ static void wgrad_split_plan(const EquivConv& e, int* splits, long long* p_per_s
   long long max_s = ceil_div64(P, min_pix);
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
-  if (s > 512) s = 512;
+  if (s > 64) s = 64;
   long long pps = ceil_div64(ceil_div64(P, s), W_BP) * W_BP;
   s = ceil_div64(P, pps);
   *splits = (int)s;

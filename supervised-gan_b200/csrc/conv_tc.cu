@@ -1,11 +1,384 @@
-// tcgen05 / TMEM implicit-GEMM convolution (placeholder until the tensor-core path lands).
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (SGK_TF32): the gather GEMM of conv_plan.h
+//   out[128 pixels x BN channels] += A[128 x 32] * B[BN x 32]^T      per k-block (one tap, 32 channels)
+// with fp32 storage, kind::tf32 tensor-core math and fp32 accumulation in tensor memory.
+//
+// CTA = 192 threads, one 128-pixel M tile x one BN-channel N tile, 2 CTAs resident per SM (the prologue /
+// epilogue of one overlaps the main loop of the other):
+//   warps 0-3  A producers: thread r owns tile row r (one output pixel).  Per k-block it gathers the 128 B of
+//              its input pixel for the current tap with 8 x cp.async(16 B, zero-fill when the tap falls in the
+//              padding / beyond the image) straight into the canonical K-major SWIZZLE_128B layout
+//              (row r at r*128, 16-B chunk c at (c ^ (r & 7))), then -- once the copies have landed
+//              (cp.async.wait_group, lagged) -- fence.proxy.async and arrive on the stage's full barrier.
+//              After the main loop the same warps are the epilogue (warp w reads TMEM lanes 32w..32w+31).
+//   warp 4     allocates tensor memory; lane 0 streams the packed weights [Co][K] with TMA
+//              (cp.async.bulk.tensor.2d, 128B swizzle, box 32 x BN) onto the same full barrier.
+//   warp 5     lane 0 issues 4 x tcgen05.mma (M128, N=BN, K=8) per k-block and tcgen05.commit's the stage back
+//              to the producers; after the last k-block it commits the accumulator to the epilogue.
+// Epilogue: tcgen05.ld 32 columns at a time, bias + activation in registers, 128-B contiguous NHWC stores.
 #include "conv_plan.h"
+#include <cuda.h>
+
 namespace sgk {
-int conv_fwd_tc(const SgkConvDesc*, const GatherPlan&, const float*, const float*, const float*, float*, int, float,
-                cudaStream_t) {
-  return SGK_EUNSUPPORTED;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024)   [46,48) version = 1   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format TF32 (2) @7/@10,
+// a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24
+__host__ __device__ inline uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct alignas(64) TcMaps {
+  CUtensorMap w[4];  // packed weights of each phase: 2-D [Co rows][K], box {32, BN}, SWIZZLE_128B
+};
+
+struct TcParams {
+  const float* in;
+  const float* bias;
+  float* out;
+  int N, Hi, Wi, Cg, Ho, Wo, Co;
+  int act;
+  float slope;
+  int nphase;
+  GatherPhase ph[4];
+  int BN, stages, tmem_cols;
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * 128;  // 128 rows x 32 fp32
+
+template <int LAG>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMaps maps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.BN * 128u;
+  const uint32_t bar_base = smem_base + (uint32_t)S * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (uint32_t)(2 * S);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+  // ---- phase of this M tile
+  int phi = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < p.nphase && (int)blockIdx.x >= p.ph[i].m_tile_begin) phi = i;
+  const GatherPhase P = p.ph[phi];
+  const int HWp = P.Hp * P.Wp;
+  const long long M = (long long)p.N * HWp;
+  const long long m0 = (long long)(blockIdx.x - P.m_tile_begin) * TC_BM;
+  const int n0 = blockIdx.y * p.BN;
+  const int cchunks = p.Cg >> 5;
+  const int KB = P.ta * P.tb * cchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 128 + 1);  // 128 A-producer threads + the TMA thread's arrive.expect_tx
+      mbar_init(empty_bar(s), 1);       // one tcgen05.commit
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_acc;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    // =============================================================== A producers, then epilogue
+    const int r = threadIdx.x;  // tile row == TMEM lane
+    const long long m = m0 + r;
+    const bool row_ok = m < M;
+    int n = 0, oy = 0, ox = 0;
+    if (row_ok) {
+      n = (int)(m / HWp);
+      int rem = (int)(m - (long long)n * HWp);
+      oy = rem / P.Wp;
+      ox = rem - oy * P.Wp;
+    }
+    const int iy0 = oy * P.is + P.ioy, ix0 = ox * P.is + P.iox;
+    const float* __restrict__ in_n = p.in + (long long)n * p.Hi * p.Wi * p.Cg;
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+    int a = 0, b = 0, c0 = 0;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % S;
+      mbar_wait(empty_bar(s), (uint32_t)(((kb / S) & 1) ^ 1));
+      const int iy = iy0 + a, ix = ix0 + b;
+      const bool ok = row_ok && (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
+      const float* src = ok ? in_n + ((long long)iy * p.Wi + ix) * p.Cg + c0 : p.in;
+      const uint32_t nbytes = ok ? 16u : 0u;
+      const uint32_t dst = smem_base + (uint32_t)s * stage_bytes + row_off;
+#pragma unroll
+      for (uint32_t j = 0; j < 8; ++j) cp_async16_zfill(dst + ((j ^ sw) << 4), src + (ok ? 4 * j : 0), nbytes);
+      cp_async_commit();
+      if (kb >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        mbar_arrive(full_bar((kb - LAG) % S));
+      }
+      c0 += 32;
+      if (c0 == p.Cg) {
+        c0 = 0;
+        if (++b == P.tb) { b = 0; ++a; }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int kb = (KB > LAG ? KB - LAG : 0); kb < KB; ++kb) mbar_arrive(full_bar(kb % S));
+
+    // ---- epilogue: TMEM -> registers -> bias/activation -> NHWC global
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    float* __restrict__ orow = nullptr;
+    if (row_ok)
+      orow = p.out + (((long long)n * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co + n0;
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    for (int cc = 0; cc < p.BN; cc += 32) {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + (uint32_t)cc, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cc + j));
+          o.x = act_apply(__uint_as_float(v[j + 0]) + bv.x, p.act, p.slope);
+          o.y = act_apply(__uint_as_float(v[j + 1]) + bv.y, p.act, p.slope);
+          o.z = act_apply(__uint_as_float(v[j + 2]) + bv.z, p.act, p.slope);
+          o.w = act_apply(__uint_as_float(v[j + 3]) + bv.w, p.act, p.slope);
+          *reinterpret_cast<float4*>(orow + cc + j) = o;
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // =============================================================== weight TMA producer
+    if (lane == 0) {
+      const void* tmap = &maps.w[phi];
+      const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % S;
+        mbar_wait(empty_bar(s), (uint32_t)(((kb / S) & 1) ^ 1));
+        mbar_arrive_expect_tx(full_bar(s), b_bytes);
+        tma_load_2d(smem_base + (uint32_t)s * stage_bytes + TC_A_BYTES, tmap, kb * 32, n0, full_bar(s));
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % S;
+        mbar_wait(full_bar(s), (uint32_t)((kb / S) & 1));
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t b_addr = a_addr + TC_A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          umma_tf32(tmem_acc, make_sw128_kmajor_desc(a_addr + kk * 32), make_sw128_kmajor_desc(b_addr + kk * 32), idesc,
+                    (uint32_t)((kb | kk) != 0));
+        }
+        umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);   // accumulator complete
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static int pick_bn(int Co) {
+  for (int bn : {256, 128, 64, 32})
+    if (Co % bn == 0) return bn;
+  return 0;
+}
+
+int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, const float* w, const float* bias, float* out,
+                int act, float slope, cudaStream_t st) {
+  if (d->precision != SGK_TF32) return SGK_EUNSUPPORTED;  // bf16 operands: not built yet
+  if ((g.Cg % 32) != 0 || (g.Co % 32) != 0) return SGK_EUNSUPPORTED;  // thin-channel layers: CUDA-core path
+  const int BN = pick_bn(g.Co);
+  if (BN == 0) return SGK_EUNSUPPORTED;
+  for (int i = 0; i < g.nphase; ++i)
+    if (g.ph[i].ta * g.ph[i].tb == 0) return SGK_EUNSUPPORTED;
+  EncodeTiledFn encode = get_encode_tiled();
+  if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled not available from the driver"); return SGK_ECUDA; }
+
+  TcParams p{};
+  TcMaps maps{};
+  p.in = in; p.bias = bias; p.out = out;
+  p.N = g.N; p.Hi = g.Hi; p.Wi = g.Wi; p.Cg = g.Cg; p.Ho = g.Ho; p.Wo = g.Wo; p.Co = g.Co;
+  p.act = act; p.slope = slope; p.nphase = g.nphase;
+  p.BN = BN;
+  p.tmem_cols = BN < 32 ? 32 : BN;
+  const uint32_t stage_bytes = TC_A_BYTES + BN * 128;
+  int stages = (int)(98304 / stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  long long tiles = 0;
+  for (int i = 0; i < g.nphase; ++i) {
+    p.ph[i] = g.ph[i];
+    p.ph[i].m_tile_begin = (int)tiles;
+    tiles += ceil_div64((long long)g.N * g.ph[i].Hp * g.ph[i].Wp, TC_BM);
+    const long long K = (long long)g.ph[i].ta * g.ph[i].tb * g.Cg;
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)g.Co};
+    cuuint64_t gstr[1] = {(cuuint64_t)K * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = encode(&maps.w[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(w + g.ph[i].w_off), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return SGK_ECUDA; }
+  }
+  if (tiles == 0) return SGK_OK;
+  if (tiles > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return SGK_EUNSUPPORTED; }
+  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 2) + 1024;
+  static bool attr_done[2] = {false, false};
+  dim3 grid((unsigned)tiles, (unsigned)(g.Co / BN));
+  if (stages == 2) {
+    if (!attr_done[0]) {
+      cudaError_t e = cudaFuncSetAttribute(conv_gather_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_gather_tc_kernel<1>)");
+      attr_done[0] = true;
+    }
+    conv_gather_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(p, maps);
+  } else {
+    if (!attr_done[1]) {
+      cudaError_t e = cudaFuncSetAttribute(conv_gather_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_gather_tc_kernel<2>)");
+      attr_done[1] = true;
+    }
+    conv_gather_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(p, maps);
+  }
+  SGK_LAUNCH_CHECK("conv_gather_tc_kernel");
+  return SGK_OK;
+}
+
 int conv_wgrad_tc(const SgkConvDesc*, const float*, const float*, float*, void*, size_t, cudaStream_t) {
-  return SGK_EUNSUPPORTED;
+  return SGK_EUNSUPPORTED;  // falls through to the CUDA-core split-K kernel until the MN-major tcgen05 wgrad lands
 }
+
 }  // namespace sgk

@@ -127,11 +127,13 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
   }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int C, int chunks) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per column
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   float s = 0.f;
-  for (int k = 0; k < chunks; ++k) s += part[(long long)k * C + c];
-  out[c] = s;
+  for (int k = lane; k < chunks; k += 32) s += part[(long long)k * C + c];
+  s = warp_sum(s);
+  if (lane == 0) out[c] = s;
 }
 
 // ---------------------------------------------------------------- NHWC concat / split
@@ -237,7 +239,7 @@ extern "C" int sgk_bias_grad(const float* dy, float* db, size_t rows, int C, voi
   colsum_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, (float*)workspace, C, g.cols, g.rlanes, (long long)rows,
                                                                 g.rows_per_chunk);
   SGK_LAUNCH_CHECK("colsum_partial_kernel");
-  colsum_final_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>((const float*)workspace, db, C, g.chunks);
+  colsum_final_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>((const float*)workspace, db, C, g.chunks);
   SGK_LAUNCH_CHECK("colsum_final_kernel");
   return SGK_OK;
 }

@@ -130,19 +130,24 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict
   }
 }
 
+// one warp per (group, channel): lanes stride over the chunk partials, fixed-order shuffle reduction
 __global__ void norm_finalize_kernel(const float* __restrict__ x, const float* __restrict__ part, float* __restrict__ stats,
                                      float* running_mean, float* running_var, float momentum, float eps, int C,
                                      long long rows, int chunks, int groups) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (idx >= groups * C) return;
-  int group = idx / C, c = idx - group * C;
-  float K = x[(long long)group * rows * C + c];
+  const int group = idx / C, c = idx - group * C;
   float s1 = 0.f, s2 = 0.f;
-  for (int k = 0; k < chunks; ++k) {
+  for (int k = lane; k < chunks; k += 32) {
     const float* p = part + (((long long)group * chunks + k) * C + c) * 2;
     s1 += p[0];
     s2 += p[1];
   }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane != 0) return;
+  const float K = x[(long long)group * rows * C + c];
   float inv_n = 1.f / (float)rows;
   float d = s1 * inv_n;
   float mean = K + d;
@@ -274,15 +279,19 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
 // sums[(group*C + c)*2] = (mean(g), mean(g*xhat));  dgamma/dbeta for the affine (batch-norm) case
 __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ sums, float* dgamma,
                                          float* dbeta, int C, long long rows, int chunks, int groups) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (idx >= groups * C) return;
-  int group = idx / C, c = idx - group * C;
+  const int group = idx / C, c = idx - group * C;
   float s1 = 0.f, s2 = 0.f;
-  for (int k = 0; k < chunks; ++k) {
+  for (int k = lane; k < chunks; k += 32) {
     const float* p = part + (((long long)group * chunks + k) * C + c) * 2;
     s1 += p[0];
     s2 += p[1];
   }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane != 0) return;
   if (dgamma != nullptr && groups == 1) { dgamma[c] = s2; dbeta[c] = s1; }
   float inv_n = 1.f / (float)rows;
   sums[idx * 2 + 0] = s1 * inv_n;
@@ -363,7 +372,7 @@ extern "C" int sgk_norm_act_fwd(const float* x, float* y, float* stats, const fl
   else norm_stats_kernel<1><<<grid, 256, smem, st>>>(x, part, C, g.cols, g.rlanes, g.rows, g.chunks, g.rows_per_chunk);
   SGK_LAUNCH_CHECK("norm_stats_kernel");
   int gc = g.groups * C;
-  norm_finalize_kernel<<<ceil_div(gc, 128), 128, 0, st>>>(x, part, stats, running_mean, running_var, momentum, eps, C,
+  norm_finalize_kernel<<<ceil_div(gc, 4), 128, 0, st>>>(x, part, stats, running_mean, running_var, momentum, eps, C,
                                                           g.rows, g.chunks, g.groups);
   SGK_LAUNCH_CHECK("norm_finalize_kernel");
   long long total4 = (long long)N * H * W * g.C4;
@@ -397,7 +406,7 @@ extern "C" int sgk_norm_act_bwd(const float* dy, const float* x, const float* st
                                                           g.chunks, g.rows_per_chunk, act, slope);
   SGK_LAUNCH_CHECK("norm_bwd_reduce_kernel");
   int gc = g.groups * C;
-  norm_bwd_finalize_kernel<<<ceil_div(gc, 128), 128, 0, st>>>(part, sums, dgamma, dbeta, C, g.rows, g.chunks, g.groups);
+  norm_bwd_finalize_kernel<<<ceil_div(gc, 4), 128, 0, st>>>(part, sums, dgamma, dbeta, C, g.rows, g.chunks, g.groups);
   SGK_LAUNCH_CHECK("norm_bwd_finalize_kernel");
   long long total4 = (long long)N * H * W * g.C4;
   long long blocks = ceil_div64(total4, 256 * 4);
