@@ -554,7 +554,7 @@ static void wgrad_split_plan(const EquivConv& e, int* splits, long long* p_per_s
   long long max_s = ceil_div64(P, min_pix);
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
-  if (s > 64) s = 64;
+  if (s > 512) s = 512;
   long long pps = ceil_div64(ceil_div64(P, s), W_BP) * W_BP;
   s = ceil_div64(P, pps);
   *splits = (int)s;
@@ -591,6 +591,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
                 int act, float slope, cudaStream_t st);  // conv_tc.cu; returns SGK_EUNSUPPORTED if shape not covered
 int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t st);
+size_t conv_wgrad_tc_workspace_bytes(const SgkConvDesc* d);
 }
 
 static int conv_gather_dispatch(const SgkConvDesc* d, int op, const float* in, const float* w, const float* bias,
@@ -624,7 +625,9 @@ extern "C" size_t sgk_conv_wgrad_workspace_bytes(const SgkConvDesc* d) {
   wgrad_split_plan(e, &splits, &pps);
   size_t a = (size_t)splits * e.O * e.I * e.k * e.k * sizeof(float);
   size_t b = sgk_bias_grad_workspace_bytes((size_t)d->N * d->Hout * d->Wout, d->Cout);
-  return a > b ? a : b;
+  size_t c = d->precision != SGK_FP32 ? conv_wgrad_tc_workspace_bytes(d) : 0;
+  a = a > b ? a : b;
+  return a > c ? a : c;
 }
 
 extern "C" int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float* dy, float* dw, float* dbias,

@@ -17,6 +17,7 @@
 // Epilogue: tcgen05.ld 32 columns at a time, bias + activation in registers, 128-B contiguous NHWC stores.
 #include "conv_plan.h"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace sgk {
 
@@ -377,8 +378,282 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   return SGK_OK;
 }
 
-int conv_wgrad_tc(const SgkConvDesc*, const float*, const float*, float*, void*, size_t, cudaStream_t) {
-  return SGK_EUNSUPPORTED;  // falls through to the CUDA-core split-K kernel until the MN-major tcgen05 wgrad lands
+// ================================================================================================
+// weight gradient on tcgen05:  dWp[m][(tap, c)] = sum_pixels G[pix][m] * X[gather(pix, tap)][c]
+// GEMM per tap with the PIXELS as the reduction dimension: D[128 m x Nc] += G^T[m x 8 pix] * Xg[8 pix x c].
+// Both operands are "MN-major" (channels contiguous, reduction index strided); for 32-bit operands tcgen05 accepts
+// exactly one such layout, SWIZZLE_128B_BASE32B: the smem image is [pixel row][32 channels = 128 B] whose 32-B chunks
+// are XOR-ed with (row & 3); 4 pixel rows form an atom (SBO = 512 B apart), one MMA consumes 8 pixels, and channel
+// groups of 32 sit LBO = 4096 B apart (32-pixel stages).  TMA writes the same image with SWIZZLE_128B_ATOM_32B.
+//   warps 0-3  gather X for the CTA's TT taps (cp.async, zero-fill), later the epilogue (lane = out channel m)
+//   warp 4     TMEM alloc; lane 0 TMA-loads the G tile (plain 2-D [pixels][Cm] matrix, 4 boxes of 32 x 32)
+//   warp 5     lane 0 issues TT x 4 MMAs per 32-pixel stage into TT accumulators (TT * Nc <= 256 TMEM columns)
+// Pixels are split across CTAs (grid.z); partials are reduced in a fixed order by wgrad_reduce_kernel.
+// ================================================================================================
+// MN-major 32-bit operands have exactly one legal smem layout: SWIZZLE_128B_BASE32B (cute: Swizzle<2,5,2>, atom =
+// 128 B of channels x 4 reduction rows): 32-byte chunks of a 128-B row are XOR-ed with (row & 3).
+__device__ __forceinline__ uint64_t make_sw128b32_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // between 32-channel groups
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // between 4-pixel groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                             // LayoutType::SWIZZLE_128B_BASE32B
+  return d;
+}
+__host__ __device__ inline uint32_t make_idesc_tf32_mn(int M, int N) {
+  return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);  // A and B MN-major
+}
+
+struct alignas(64) WTcMap {
+  CUtensorMap g;  // G as a 2-D matrix [P pixels][Cm], box {32 channels, 32 pixels}, SWIZZLE_128B
+};
+struct WTcParams {
+  const float* x;
+  float* part;
+  int N, Hg, Wg, Cm, Hx, Wx, Cx, k, s, off, K;
+  long long P, p_per_split;
+  int TT, Nc, tmem_cols;
+  int variant;
+};
+constexpr int WTC_P = 32;                       // pixels per stage
+constexpr int WTC_BLK = WTC_P * 128;            // one 32-channel block of a stage: 4096 B
+constexpr int WTC_A_BYTES = 4 * WTC_BLK;        // 128 G channels
+constexpr int WTC_STAGES = 2;
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant__ WTcMap map) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int S = WTC_STAGES;
+  const int ncg = p.Nc >> 5;                                       // 32-channel groups per tap
+  const uint32_t b_bytes = (uint32_t)p.TT * (uint32_t)ncg * WTC_BLK;
+  const uint32_t stage_bytes = WTC_A_BYTES + b_bytes;
+  const uint32_t bar_base = smem_base + S * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (uint32_t)(2 * S);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+  // column tile: taps [t0, t0+TT) x channels [c0, c0+Nc)
+  const int ctiles = p.Cx / p.Nc;
+  const int t0 = ((int)blockIdx.x / ctiles) * p.TT;
+  const int c0 = ((int)blockIdx.x % ctiles) * p.Nc;
+  const int mch0 = blockIdx.y * 128;
+  const long long pbeg = (long long)blockIdx.z * p.p_per_split;
+  long long pend = pbeg + p.p_per_split;
+  if (pend > p.P) pend = p.P;
+  const int steps = pend > pbeg ? (int)((pend - pbeg + WTC_P - 1) / WTC_P) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 128 + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_acc;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    // =============================================================== X gather producers
+    const int q = threadIdx.x & 31;   // pixel row within the stage
+    const int sub = threadIdx.x >> 5;  // 4 threads share a pixel: they split the (tap, channel-group) chunks
+    const int HWg = p.Hg * p.Wg;
+    const int nchunks = p.TT * ncg;
+    const uint32_t sw = (uint32_t)(q & 3);   // Swizzle<2,5,2>: 32-B chunk index ^= pixel row & 3
+    for (int st = 0; st < steps; ++st) {
+      const int s = st % S;
+      mbar_wait(empty_bar(s), (uint32_t)(((st / S) & 1) ^ 1));
+      const long long pix = pbeg + (long long)st * WTC_P + q;
+      const bool pok = pix < pend;
+      int n = 0, oy = 0, ox = 0;
+      if (pok) {
+        n = (int)(pix / HWg);
+        int rem = (int)(pix - (long long)n * HWg);
+        oy = rem / p.Wg;
+        ox = rem - oy * p.Wg;
+      }
+      const float* __restrict__ xn = p.x + (long long)n * p.Hx * p.Wx * p.Cx;
+      const uint32_t bbase = smem_base + (uint32_t)s * stage_bytes + WTC_A_BYTES + (uint32_t)q * 128u;
+      for (int ch = sub; ch < nchunks; ch += 4) {
+        const int ti = ch / ncg, cg = ch - ti * ncg;
+        const int tap = t0 + ti;
+        const int a = tap / p.k, b = tap - a * p.k;
+        const int iy = oy * p.s + a + p.off, ix = ox * p.s + b + p.off;
+        const bool ok = pok && (unsigned)iy < (unsigned)p.Hx && (unsigned)ix < (unsigned)p.Wx;
+        const float* src = ok ? xn + ((long long)iy * p.Wx + ix) * p.Cx + c0 + cg * 32 : p.x;
+        const uint32_t nbytes = ok ? 16u : 0u;
+        const uint32_t dst = bbase + (uint32_t)ch * WTC_BLK;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j)
+          cp_async16_zfill(dst + ((((j >> 1) ^ sw) << 5) | ((j & 1) << 4)), src + (ok ? 4 * j : 0), nbytes);
+      }
+      cp_async_commit();
+      if (st >= 1) {
+        cp_async_wait<1>();
+        fence_proxy_async();
+        mbar_arrive(full_bar((st - 1) % S));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    if (steps > 0) mbar_arrive(full_bar((steps - 1) % S));
+
+    // ---- epilogue: lane = out channel m; columns = (tap, c)
+    if (steps > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const int m = mch0 + threadIdx.x;
+    const bool mok = m < p.Cm;
+    float* __restrict__ prow = p.part + ((long long)blockIdx.z * p.Cm + (mok ? m : 0)) * p.K;
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    const int ncols = p.TT * p.Nc;
+    for (int cc = 0; cc < ncols; cc += 32) {
+      uint32_t v[32];
+      if (steps > 0) {
+        tmem_ld32(lane_addr + (uint32_t)cc, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (mok) {
+        const int ti = cc / p.Nc, cin = cc - ti * p.Nc;
+        float* dstp = prow + (long long)(t0 + ti) * p.Cx + c0 + cin;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dstp + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                             __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+  } else if (warp == 4) {
+    // =============================================================== G tile via TMA
+    if (lane == 0) {
+      for (int st = 0; st < steps; ++st) {
+        const int s = st % S;
+        mbar_wait(empty_bar(s), (uint32_t)(((st / S) & 1) ^ 1));
+        mbar_arrive_expect_tx(full_bar(s), WTC_A_BYTES);
+        const long long row = pbeg + (long long)st * WTC_P;
+        const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4)
+          tma_load_2d(abase + g4 * WTC_BLK, &map.g, mch0 + g4 * 32, (int)row, full_bar(s));
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32_mn(128, p.Nc);
+      for (int st = 0; st < steps; ++st) {
+        const int s = st % S;
+        mbar_wait(full_bar(s), (uint32_t)((st / S) & 1));
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t b_addr = a_addr + WTC_A_BYTES;
+        for (int ti = 0; ti < p.TT; ++ti) {
+#pragma unroll
+          for (int kg = 0; kg < 4; ++kg) {
+            const uint32_t lbo = (uint32_t)WTC_BLK, sbo = (p.variant & 1) ? 1024u : 512u;
+            umma_tf32(tmem_acc + (uint32_t)(ti * p.Nc), make_sw128b32_mnmajor_desc(a_addr + kg * 1024, lbo, sbo),
+                      make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(ti * ncg) * WTC_BLK + kg * 1024, lbo, sbo), idesc,
+                      (uint32_t)((st | kg) != 0));
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      if (steps > 0) umma_commit(tmem_full_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+}
+
+// plan shared by the workspace query and the launch
+struct WTcPlan { int ok, TT, Nc, tmem_cols, splits; long long pps; };
+static WTcPlan wgrad_tc_plan(const EquivConv& e) {
+  WTcPlan w{};
+  if ((e.I % 32) != 0 || (e.O % 32) != 0) return w;
+  const int taps = e.k * e.k;
+  int Nc = e.I >= 256 && e.I % 256 == 0 ? 256 : (e.I % 128 == 0 ? 128 : (e.I % 64 == 0 ? 64 : 32));
+  int TT = 256 / Nc;
+  while (TT > 1 && (taps % TT) != 0) TT >>= 1;
+  w.Nc = Nc; w.TT = TT;
+  int cols = TT * Nc;
+  w.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : 256));
+  const long long P = (long long)e.N * e.Hs * e.Ws;
+  const long long tiles = (long long)(taps / TT) * (e.I / Nc) * ceil_div(e.O, 128);
+  long long s = ceil_div64(2LL * 2 * sm_count(), tiles);
+  long long maxs = ceil_div64(P, 8 * WTC_P);
+  if (s > maxs) s = maxs;
+  if (s < 1) s = 1;
+  if (s > 256) s = 256;
+  w.pps = ceil_div64(ceil_div64(P, s), WTC_P) * WTC_P;
+  w.splits = (int)ceil_div64(P, w.pps);
+  w.ok = 1;
+  return w;
+}
+
+size_t conv_wgrad_tc_workspace_bytes(const SgkConvDesc* d) {
+  EquivConv e = equiv_conv(*d);
+  WTcPlan w = wgrad_tc_plan(e);
+  if (!w.ok) return 0;
+  return (size_t)w.splits * e.O * e.I * e.k * e.k * sizeof(float);
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int O, int I, int k, int splits);
+
+int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  if (d->precision != SGK_TF32) return SGK_EUNSUPPORTED;
+  EquivConv e = equiv_conv(*d);
+  WTcPlan w = wgrad_tc_plan(e);
+  if (!w.ok) return SGK_EUNSUPPORTED;
+  EncodeTiledFn encode = get_encode_tiled();
+  if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled not available from the driver"); return SGK_ECUDA; }
+  const size_t need = (size_t)w.splits * e.O * e.I * e.k * e.k * sizeof(float);
+  if (need > ws_bytes) { set_error("sgk_conv_wgrad(tc): workspace %zu < %zu", ws_bytes, need); return SGK_EWORKSPACE; }
+  WTcParams p{};
+  WTcMap map{};
+  const float* g = d->transposed ? x : dy;   // O-side tensor (small grid), un-gathered
+  p.x = d->transposed ? dy : x;              // I-side tensor (big grid), gathered
+  p.part = (float*)ws;
+  p.N = e.N; p.Hg = e.Hs; p.Wg = e.Ws; p.Cm = e.O; p.Hx = e.Hb; p.Wx = e.Wb; p.Cx = e.I;
+  p.k = e.k; p.s = e.s; p.off = -e.p; p.K = e.k * e.k * e.I;
+  p.P = (long long)e.N * e.Hs * e.Ws; p.p_per_split = w.pps;
+  p.TT = w.TT; p.Nc = w.Nc; p.tmem_cols = w.tmem_cols;
+  { const char* ev = getenv("SGK_WGRAD_VARIANT"); p.variant = ev ? atoi(ev) : 0; }
+  cuuint64_t gdim[2] = {(cuuint64_t)e.O, (cuuint64_t)p.P};
+  cuuint64_t gstr[1] = {(cuuint64_t)e.O * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)WTC_P};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = encode(&map.g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)g, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(G) failed (%d)", (int)r); return SGK_ECUDA; }
+  const uint32_t stage_bytes = WTC_A_BYTES + (uint32_t)w.TT * (w.Nc / 32) * WTC_BLK;
+  const size_t smem = (size_t)WTC_STAGES * stage_bytes + 8 * (2 * WTC_STAGES + 2) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t ce = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(conv_wgrad_tc_kernel)");
+    attr_done = true;
+  }
+  dim3 grid((unsigned)((e.k * e.k / w.TT) * (e.I / w.Nc)), (unsigned)ceil_div(e.O, 128), (unsigned)w.splits);
+  conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, map);
+  SGK_LAUNCH_CHECK("conv_wgrad_tc_kernel");
+  long long total = (long long)e.O * e.I * e.k * e.k;
+  wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>((const float*)ws, dw, e.O, e.I, e.k, w.splits);
+  SGK_LAUNCH_CHECK("wgrad_reduce_kernel");
+  return SGK_OK;
 }
 
 }  // namespace sgk
