@@ -229,78 +229,98 @@ __global__ void __launch_bounds__(F_THREADS) gather_gemm_f(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
-// thin-output gather conv: Co <= 4.  One warp per output pixel, lanes split the K reduction with
-// coalesced float4 reads (NHWC keeps (b, c) contiguous for a fixed tap row), warp-shuffle reduce.
-// Used by the last PatchGAN conv (Cout = 1) and the generators' last ConvT (Cout = 1/2).
+// thin-output gather conv: Co <= 4 (HBM-bound).  LP lanes cooperate on one output pixel: for every tap they read
+// LP consecutive float4 of the pixel's channel vector (a warp reads 32/LP pixels x LP*16 B, fully coalesced), keep CO
+// partial sums, and finish with log2(LP) shuffle steps.  LP = Cg/4 capped to 32, so a 32-channel layer packs 4 pixels
+// per warp and the 256-channel PatchGAN head uses the whole warp on one pixel.
+// Used by the last PatchGAN conv (Cout = 1), the generators' last ConvT (Cout = 1/2) and the first D conv's dgrad.
 // ------------------------------------------------------------------------------------------------
-template <int CO>
-__global__ void __launch_bounds__(256) gather_thin_out(const __grid_constant__ FParams p) {
+template <int CO, int LP>
+__global__ void __launch_bounds__(256) gather_thin_out(const __grid_constant__ FParams p, long long total_pixels) {
+  constexpr int PPW = 32 / LP;  // pixels per warp
   const int lane = threadIdx.x & 31;
+  const int sub = lane / LP, l = lane % LP;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  // phase lookup by pixel prefix (m_tile_begin is reused as pixel-prefix / 8 warps... see launcher)
+  const long long gp = warp * PPW + sub;  // global pixel index over all phases
+  const bool active = gp < total_pixels;
   int phi = 0;
   long long base = 0;
   {
     long long acc_pix = 0;
     for (int i = 0; i < p.nphase; ++i) {
       long long cnt = (long long)p.N * p.ph[i].Hp * p.ph[i].Wp;
-      if (warp >= acc_pix && warp < acc_pix + cnt) { phi = i; base = acc_pix; }
+      if (gp >= acc_pix && gp < acc_pix + cnt) { phi = i; base = acc_pix; }
       acc_pix += cnt;
     }
-    if (warp >= acc_pix) return;
   }
   const GatherPhase P = p.ph[phi];
   const int HWp = P.Hp * P.Wp;
-  long long m = warp - base;
+  long long m = active ? gp - base : 0;
   int n = (int)(m / HWp);
   int rem = (int)(m - (long long)n * HWp);
   int oy = rem / P.Wp, ox = rem - oy * P.Wp;
-  int iy0 = oy * P.is + P.ioy, ix0 = ox * P.is + P.iox;
-  const int rowlen = P.tb * p.Cg;  // contiguous floats of one tap row (when fully inside)
-  const int K = P.ta * rowlen;
+  const int iy0 = oy * P.is + P.ioy, ix0 = ox * P.is + P.iox;
+  const int K = P.ta * P.tb * p.Cg;
   const float* __restrict__ W = p.w + P.w_off;
   const float* __restrict__ in_n = p.in + (long long)n * p.Hi * p.Wi * p.Cg;
   float acc[CO];
 #pragma unroll
   for (int j = 0; j < CO; ++j) acc[j] = 0.f;
   const bool vec = (p.Cg & 3) == 0;
-  for (int a = 0; a < P.ta; ++a) {
-    int iy = iy0 + a;
-    if ((unsigned)iy >= (unsigned)p.Hi) continue;
-    const float* __restrict__ row = in_n + ((long long)iy * p.Wi + ix0) * p.Cg;
-    if (vec) {
-      for (int e = lane * 4; e < rowlen; e += 128) {
-        int b = e / p.Cg;
-        int ix = ix0 + b;
+  if (active) {
+    for (int a = 0; a < P.ta; ++a) {
+      const int iy = iy0 + a;
+      if ((unsigned)iy >= (unsigned)p.Hi) continue;
+      for (int b = 0; b < P.tb; ++b) {
+        const int ix = ix0 + b;
         if ((unsigned)ix >= (unsigned)p.Wi) continue;
-        float4 v = __ldg(reinterpret_cast<const float4*>(row + e));
+        const float* __restrict__ px = in_n + ((long long)iy * p.Wi + ix) * p.Cg;
+        const int kofs = (a * P.tb + b) * p.Cg;
+        if (vec) {
+          for (int c = l * 4; c < p.Cg; c += LP * 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(px + c));
 #pragma unroll
-        for (int j = 0; j < CO; ++j) {
-          if (j < p.Co) {
-            float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)j * K + a * rowlen + e));
-            acc[j] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[j]))));
+            for (int j = 0; j < CO; ++j) {
+              if (j < p.Co) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)j * K + kofs + c));
+                acc[j] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[j]))));
+              }
+            }
+          }
+        } else {
+          for (int c = l; c < p.Cg; c += LP) {
+            const float v = __ldg(px + c);
+#pragma unroll
+            for (int j = 0; j < CO; ++j)
+              if (j < p.Co) acc[j] = fmaf(v, __ldg(W + (long long)j * K + kofs + c), acc[j]);
           }
         }
-      }
-    } else {
-      for (int e = lane; e < rowlen; e += 32) {
-        int b = e / p.Cg;
-        int ix = ix0 + b;
-        if ((unsigned)ix >= (unsigned)p.Wi) continue;
-        float v = __ldg(row + e);
-#pragma unroll
-        for (int j = 0; j < CO; ++j)
-          if (j < p.Co) acc[j] = fmaf(v, __ldg(W + (long long)j * K + a * rowlen + e), acc[j]);
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < CO; ++j) acc[j] = warp_sum(acc[j]);
-  if (lane == 0) {
+  for (int j = 0; j < CO; ++j)
+#pragma unroll
+    for (int o = LP / 2; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  if (active && l == 0) {
     float* o = p.out + (((long long)n * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co;
 #pragma unroll
     for (int j = 0; j < CO; ++j)
       if (j < p.Co) o[j] = act_apply(acc[j] + (p.bias ? __ldg(p.bias + j) : 0.f), p.act, p.slope);
+  }
+}
+
+template <int CO>
+static void launch_thin(const FParams& p, long long pixels, int Cg, cudaStream_t st) {
+  int lp = (Cg % 4 == 0) ? Cg / 4 : Cg;
+  if (lp >= 32) {
+    gather_thin_out<CO, 32><<<(unsigned)ceil_div64(pixels * 32, 256), 256, 0, st>>>(p, pixels);
+  } else if (lp >= 16) {
+    gather_thin_out<CO, 16><<<(unsigned)ceil_div64(pixels * 16, 256), 256, 0, st>>>(p, pixels);
+  } else if (lp >= 8) {
+    gather_thin_out<CO, 8><<<(unsigned)ceil_div64(pixels * 8, 256), 256, 0, st>>>(p, pixels);
+  } else {
+    gather_thin_out<CO, 4><<<(unsigned)ceil_div64(pixels * 4, 256), 256, 0, st>>>(p, pixels);
   }
 }
 
@@ -320,12 +340,10 @@ static int launch_gather(const GatherPlan& g, const float* in, const float* w, c
   }
   if (pixels == 0) return SGK_OK;
   if (g.Co <= 4) {
-    long long threads = pixels * 32;
-    long long blocks = ceil_div64(threads, 256);
-    if (blocks > 0x7fffffffLL) { set_error("conv: grid too large"); return SGK_EUNSUPPORTED; }
-    if (g.Co <= 1) gather_thin_out<1><<<(unsigned)blocks, 256, 0, st>>>(p);
-    else if (g.Co == 2) gather_thin_out<2><<<(unsigned)blocks, 256, 0, st>>>(p);
-    else gather_thin_out<4><<<(unsigned)blocks, 256, 0, st>>>(p);
+    if (pixels * 32 / 256 > 0x7fffffffLL) { set_error("conv: grid too large"); return SGK_EUNSUPPORTED; }
+    if (g.Co <= 1) launch_thin<1>(p, pixels, g.Cg, st);
+    else if (g.Co == 2) launch_thin<2>(p, pixels, g.Cg, st);
+    else launch_thin<4>(p, pixels, g.Cg, st);
     SGK_LAUNCH_CHECK("gather_thin_out");
     return SGK_OK;
   }
