@@ -244,13 +244,15 @@ def run_ours(args):
     # ---------------- roofline leg: per-launch CUDA events on the conv kernels over timed eager steps
     roof = None
     cpu = None
+    # every rank runs the instrumented steps (they contain the gradient all-reduces); only rank 0 records
+    timer = S.ops.KernelTimer() if rank == 0 else None
+    S.ops.set_kernel_timer(timer)
+    for _ in range(2):
+        m.optimize_parameters()
+    S.ops.set_kernel_timer(None)
+    barrier()
     if rank == 0:
-        timer = S.ops.KernelTimer()
-        S.ops.set_kernel_timer(timer)
-        for _ in range(2):
-            m.optimize_parameters()
         summ = timer.summary()
-        S.ops.set_kernel_timer(None)
         fam = {}
         for tag, e in summ.items():
             f = fam.setdefault(tag.split(" ")[0], {"ms": 0.0, "flops": 0.0, "launches": 0})
@@ -292,8 +294,15 @@ def run_ours(args):
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "api": "FCGANModel.set_input + optimize_parameters + get_current_errors (eager)"},
                 "roofline": roof, "cpu_baseline": cpu, "loss_G_checksum": sink / max(e2e_steps, 1)}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # a captured graph keeps NCCL work alive; tear down in a fixed order and skip the interpreter's own
+        # (occasionally hanging) NCCL finalisers
+        barrier()
+        graph = None
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
