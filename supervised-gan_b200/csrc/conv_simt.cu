@@ -545,12 +545,50 @@ __global__ void __launch_bounds__(256) pixel_reduce_w_thin(const __grid_constant
     *reinterpret_cast<float4*>(part + (long long)m * p.K + j) = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
 }
 
-// ordered reduction over splits and scatter into the reference layout raw[O][I][k][k]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int O, int I, int k, int splits) {
+// ordered reduction over splits and scatter into the reference layout raw[O][I][k][k].
+// A group of RL lanes owns 4 consecutive packed outputs (one float4 per split): lanes stride over the splits with
+// independent loads in flight, then a fixed-order shuffle reduction -- deterministic, and bandwidth- rather than
+// latency-bound when there are hundreds of splits.
+template <int RL>
+__global__ void __launch_bounds__(256) wgrad_reduce_vec_kernel(const float* __restrict__ part, float* __restrict__ dw, int O,
+                                                               int I, int k, int splits) {
+  const long long total = (long long)O * I * k * k;
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / RL;
+  const int l = threadIdx.x % RL;
+  const long long idx = gid * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx < total) {
+    for (int sp = l; sp < splits; sp += RL) {
+      const float4 v = ld_stream(reinterpret_cast<const float4*>(part + (long long)sp * total + idx));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+#pragma unroll
+  for (int o = RL / 2; o > 0; o >>= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+    s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+    s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
+    s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+  }
+  if (idx < total && l == 0) {
+    // idx enumerates the packed order [o][(a,b,i)], I % 4 == 0 so the 4 outputs share (o, a, b)
+    const int i = (int)(idx % I);
+    long long tt = idx / I;
+    const int b = (int)(tt % k);
+    tt /= k;
+    const int a = (int)(tt % k);
+    const int o = (int)(tt / k);
+    const float r[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dw[(((long long)o * I + i + j) * k + a) * k + b] = r[j];
+  }
+}
+
+__global__ void wgrad_reduce_scalar_kernel(const float* __restrict__ part, float* __restrict__ dw, int O, int I, int k,
+                                           int splits) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)O * I * k * k;
   if (idx >= total) return;
-  // idx enumerates the packed order [o][(a,b,i)] so reads are coalesced
   int i = (int)(idx % I);
   long long tt = idx / I;
   int b = (int)(tt % k);
@@ -560,6 +598,19 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   float s = 0.f;
   for (int sp = 0; sp < splits; ++sp) s += part[(long long)sp * total + idx];
   dw[(((long long)o * I + i) * k + a) * k + b] = s;
+}
+
+int launch_wgrad_reduce(const float* part, float* dw, int O, int I, int k, int splits, cudaStream_t st) {
+  const long long total = (long long)O * I * k * k;
+  if ((I & 3) == 0) {
+    const long long groups = total / 4;
+    if (splits >= 16) wgrad_reduce_vec_kernel<8><<<(unsigned)ceil_div64(groups * 8, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
+    else wgrad_reduce_vec_kernel<1><<<(unsigned)ceil_div64(groups, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
+  } else {
+    wgrad_reduce_scalar_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
+  }
+  SGK_LAUNCH_CHECK("wgrad_reduce_kernel");
+  return SGK_OK;
 }
 
 static void wgrad_split_plan(const EquivConv& e, int* splits, long long* p_per_split) {
@@ -692,8 +743,5 @@ extern "C" int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float*
     else pixel_reduce_w<false><<<grid, 256, 0, st>>>(p);
     SGK_LAUNCH_CHECK("pixel_reduce_w");
   }
-  long long total = (long long)e.O * e.I * e.k * e.k;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>((const float*)workspace, dw, e.O, e.I, e.k, splits);
-  SGK_LAUNCH_CHECK("wgrad_reduce_kernel");
-  return SGK_OK;
+  return launch_wgrad_reduce((const float*)workspace, dw, e.O, e.I, e.k, splits, st);
 }

@@ -4,17 +4,19 @@
 //
 // CTA = 192 threads, one 128-pixel M tile x one BN-channel N tile, 2 CTAs resident per SM (the prologue /
 // epilogue of one overlaps the main loop of the other):
-//   warps 0-3  A producers: thread r owns tile row r (one output pixel).  Per k-block it gathers the 128 B of
-//              its input pixel for the current tap with 8 x cp.async(16 B, zero-fill when the tap falls in the
-//              padding / beyond the image) straight into the canonical K-major SWIZZLE_128B layout
-//              (row r at r*128, 16-B chunk c at (c ^ (r & 7))), then -- once the copies have landed
-//              (cp.async.wait_group, lagged) -- fence.proxy.async and arrive on the stage's full barrier.
+//   warps 0-3  A producers.  Tile row r = one output pixel; its (image, y0, x0) is decoded once into a smem table.
+//              Per k-block every warp gathers its 32 rows with 8 cp.async(16 B, zero-fill when the tap falls in the
+//              padding / beyond the image) instructions in which lanes 8i..8i+7 copy the 8 chunks of ONE row, i.e.
+//              each instruction touches 4 x 128-B lines (not 32: L1 serves one line per wavefront), straight into
+//              the canonical K-major SWIZZLE_128B image (row r at r*128, 16-B chunk c at (c ^ (r & 7))); once the
+//              copies have landed (cp.async.wait_group, lagged): fence.proxy.async + arrive on the full barrier.
 //              After the main loop the same warps are the epilogue (warp w reads TMEM lanes 32w..32w+31).
 //   warp 4     allocates tensor memory; lane 0 streams the packed weights [Co][K] with TMA
 //              (cp.async.bulk.tensor.2d, 128B swizzle, box 32 x BN) onto the same full barrier.
 //   warp 5     lane 0 issues 4 x tcgen05.mma (M128, N=BN, K=8) per k-block and tcgen05.commit's the stage back
 //              to the producers; after the last k-block it commits the accumulator to the epilogue.
-// Epilogue: tcgen05.ld 32 columns at a time, bias + activation in registers, 128-B contiguous NHWC stores.
+// Epilogue: tcgen05.ld 32 columns at a time, bias + activation in registers, transposed through (now idle) stage
+// smem so that every global store instruction writes 4 rows x 128 contiguous bytes of the NHWC output.
 #include "conv_plan.h"
 #include <cuda.h>
 #include <stdlib.h>
@@ -171,6 +173,25 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
   const int cchunks = p.Cg >> 5;
   const int KB = P.ta * P.tb * cchunks;
 
+  // per-row tables (written once): gather origin and output address of each of the 128 tile rows
+  const uint32_t rowinfo = tmem_slot + 8u;            // int4 {image n, iy0, ix0, valid}
+  const uint32_t rowout = rowinfo + 128u * 16u;       // int64 float-offset of the output pixel (channel 0)
+  if (threadIdx.x < TC_BM) {
+    const int r = threadIdx.x;
+    const long long m = m0 + r;
+    const int ok = m < M ? 1 : 0;
+    int n = 0, oy = 0, ox = 0;
+    if (ok) {
+      n = (int)(m / HWp);
+      int rem = (int)(m - (long long)n * HWp);
+      oy = rem / P.Wp;
+      ox = rem - oy * P.Wp;
+    }
+    const int iy0 = oy * P.is + P.ioy, ix0 = ox * P.is + P.iox;
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(rowinfo + 16u * r), "r"(n), "r"(iy0), "r"(ix0), "r"(ok));
+    const long long oofs = (((long long)n * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co;
+    asm volatile("st.shared.s64 [%0], %1;" ::"r"(rowout + 8u * r), "l"(oofs));
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 128 + 1);  // 128 A-producer threads + the TMA thread's arrive.expect_tx
@@ -188,31 +209,24 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
 
   if (warp < 4) {
     // =============================================================== A producers, then epilogue
-    const int r = threadIdx.x;  // tile row == TMEM lane
-    const long long m = m0 + r;
-    const bool row_ok = m < M;
-    int n = 0, oy = 0, ox = 0;
-    if (row_ok) {
-      n = (int)(m / HWp);
-      int rem = (int)(m - (long long)n * HWp);
-      oy = rem / P.Wp;
-      ox = rem - oy * P.Wp;
-    }
-    const int iy0 = oy * P.is + P.ioy, ix0 = ox * P.is + P.iox;
-    const float* __restrict__ in_n = p.in + (long long)n * p.Hi * p.Wi * p.Cg;
-    const uint32_t row_off = (uint32_t)r * 128u;
-    const uint32_t sw = (uint32_t)(r & 7);
+    const uint32_t j = (uint32_t)(lane & 7);   // 16-B chunk of the row
+    const int rsub = lane >> 3;                // row within the group of 4 rows one instruction covers
     int a = 0, b = 0, c0 = 0;
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % S;
       mbar_wait(empty_bar(s), (uint32_t)(((kb / S) & 1) ^ 1));
-      const int iy = iy0 + a, ix = ix0 + b;
-      const bool ok = row_ok && (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
-      const float* src = ok ? in_n + ((long long)iy * p.Wi + ix) * p.Cg + c0 : p.in;
-      const uint32_t nbytes = ok ? 16u : 0u;
-      const uint32_t dst = smem_base + (uint32_t)s * stage_bytes + row_off;
+      const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
 #pragma unroll
-      for (uint32_t j = 0; j < 8; ++j) cp_async16_zfill(dst + ((j ^ sw) << 4), src + (ok ? 4 * j : 0), nbytes);
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp * 32 + i * 4 + rsub;
+        int n, iy, ix, ok;
+        asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(n), "=r"(iy), "=r"(ix), "=r"(ok) : "r"(rowinfo + 16u * r));
+        iy += a;
+        ix += b;
+        const bool good = ok && (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
+        const float* src = good ? p.in + (((long long)n * p.Hi + iy) * p.Wi + ix) * p.Cg + c0 + 4 * j : p.in;
+        cp_async16_zfill(abase + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4), src, good ? 16u : 0u);
+      }
       cp_async_commit();
       if (kb >= LAG) {
         cp_async_wait<LAG>();
@@ -229,30 +243,44 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
     fence_proxy_async();
     for (int kb = (KB > LAG ? KB - LAG : 0); kb < KB; ++kb) mbar_arrive(full_bar(kb % S));
 
-    // ---- epilogue: TMEM -> registers -> bias/activation -> NHWC global
+    // ---- epilogue: TMEM -> registers -> bias/activation -> smem transpose -> coalesced NHWC global stores
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    float* __restrict__ orow = nullptr;
-    if (row_ok)
-      orow = p.out + (((long long)n * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co + n0;
+    const int r_own = warp * 32 + lane;                       // tile row == TMEM lane of this thread
+    const uint32_t stg = smem_base;                           // stage 0's A region: 128 rows x 128 B, idle now
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
     for (int cc = 0; cc < p.BN; cc += 32) {
       uint32_t v[32];
       tmem_ld32(lane_addr + (uint32_t)cc, v);
       tmem_ld_wait();
-      if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cc + j));
-          o.x = act_apply(__uint_as_float(v[j + 0]) + bv.x, p.act, p.slope);
-          o.y = act_apply(__uint_as_float(v[j + 1]) + bv.y, p.act, p.slope);
-          o.z = act_apply(__uint_as_float(v[j + 2]) + bv.z, p.act, p.slope);
-          o.w = act_apply(__uint_as_float(v[j + 3]) + bv.w, p.act, p.slope);
-          *reinterpret_cast<float4*>(orow + cc + j) = o;
-        }
+      for (int q = 0; q < 8; ++q) {
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cc + 4 * q));
+        const float o0 = act_apply(__uint_as_float(v[4 * q + 0]) + bv.x, p.act, p.slope);
+        const float o1 = act_apply(__uint_as_float(v[4 * q + 1]) + bv.y, p.act, p.slope);
+        const float o2 = act_apply(__uint_as_float(v[4 * q + 2]) + bv.z, p.act, p.slope);
+        const float o3 = act_apply(__uint_as_float(v[4 * q + 3]) + bv.w, p.act, p.slope);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r_own * 128u +
+                                                                    (((uint32_t)q ^ (uint32_t)(r_own & 7)) << 4)),
+                     "f"(o0), "f"(o1), "f"(o2), "f"(o3)
+                     : "memory");
       }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp * 32 + i * 4 + rsub;
+        long long oofs;
+        int ok;
+        asm volatile("ld.shared.s64 %0, [%1];" : "=l"(oofs) : "r"(rowout + 8u * r));
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ok) : "r"(rowinfo + 16u * r + 12u));
+        float4 o;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                     : "r"(stg + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
+        if (ok) *reinterpret_cast<float4*>(p.out + oofs + n0 + cc + 4 * j) = o;
+      }
+      __syncwarp();
     }
   } else if (warp == 4) {
     // =============================================================== weight TMA producer
@@ -356,7 +384,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   }
   if (tiles == 0) return SGK_OK;
   if (tiles > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return SGK_EUNSUPPORTED; }
-  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 2) + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 2) + 128 * 24 + 1024;
   static bool attr_done[2] = {false, false};
   dim3 grid((unsigned)tiles, (unsigned)(g.Co / BN));
   if (stages == 2) {
@@ -463,37 +491,44 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
 
   if (warp < 4) {
     // =============================================================== X gather producers
-    const int q = threadIdx.x & 31;   // pixel row within the stage
-    const int sub = threadIdx.x >> 5;  // 4 threads share a pixel: they split the (tap, channel-group) chunks
+    // 8 lanes copy the 8 chunks of one 128-B (pixel, tap, channel-group) row: every cp.async instruction covers
+    // 4 rows = 4 x 128-B lines.  Thread t serves rows q = (t>>3) and (t>>3)+16 of every chunk.
+    const uint32_t j = (uint32_t)(threadIdx.x & 7);
+    const int grp = threadIdx.x >> 3;  // 0..15
     const int HWg = p.Hg * p.Wg;
     const int nchunks = p.TT * ncg;
-    const uint32_t sw = (uint32_t)(q & 3);   // Swizzle<2,5,2>: 32-B chunk index ^= pixel row & 3
     for (int st = 0; st < steps; ++st) {
       const int s = st % S;
       mbar_wait(empty_bar(s), (uint32_t)(((st / S) & 1) ^ 1));
-      const long long pix = pbeg + (long long)st * WTC_P + q;
-      const bool pok = pix < pend;
-      int n = 0, oy = 0, ox = 0;
-      if (pok) {
-        n = (int)(pix / HWg);
-        int rem = (int)(pix - (long long)n * HWg);
-        oy = rem / p.Wg;
-        ox = rem - oy * p.Wg;
+      int pn[2], poy[2], pox[2];
+      bool pok[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long pix = pbeg + (long long)st * WTC_P + grp + 16 * h;
+        pok[h] = pix < pend;
+        pn[h] = 0; poy[h] = 0; pox[h] = 0;
+        if (pok[h]) {
+          pn[h] = (int)(pix / HWg);
+          int rem = (int)(pix - (long long)pn[h] * HWg);
+          poy[h] = rem / p.Wg;
+          pox[h] = rem - poy[h] * p.Wg;
+        }
       }
-      const float* __restrict__ xn = p.x + (long long)n * p.Hx * p.Wx * p.Cx;
-      const uint32_t bbase = smem_base + (uint32_t)s * stage_bytes + WTC_A_BYTES + (uint32_t)q * 128u;
-      for (int ch = sub; ch < nchunks; ch += 4) {
+      const uint32_t bbase = smem_base + (uint32_t)s * stage_bytes + WTC_A_BYTES;
+      for (int ch = 0; ch < nchunks; ++ch) {
         const int ti = ch / ncg, cg = ch - ti * ncg;
         const int tap = t0 + ti;
         const int a = tap / p.k, b = tap - a * p.k;
-        const int iy = oy * p.s + a + p.off, ix = ox * p.s + b + p.off;
-        const bool ok = pok && (unsigned)iy < (unsigned)p.Hx && (unsigned)ix < (unsigned)p.Wx;
-        const float* src = ok ? xn + ((long long)iy * p.Wx + ix) * p.Cx + c0 + cg * 32 : p.x;
-        const uint32_t nbytes = ok ? 16u : 0u;
-        const uint32_t dst = bbase + (uint32_t)ch * WTC_BLK;
 #pragma unroll
-        for (uint32_t j = 0; j < 8; ++j)
-          cp_async16_zfill(dst + ((((j >> 1) ^ sw) << 5) | ((j & 1) << 4)), src + (ok ? 4 * j : 0), nbytes);
+        for (int h = 0; h < 2; ++h) {
+          const int q = grp + 16 * h;
+          const int iy = poy[h] * p.s + a + p.off, ix = pox[h] * p.s + b + p.off;
+          const bool ok = pok[h] && (unsigned)iy < (unsigned)p.Hx && (unsigned)ix < (unsigned)p.Wx;
+          const float* src = ok ? p.x + (((long long)pn[h] * p.Hx + iy) * p.Wx + ix) * p.Cx + c0 + cg * 32 + 4 * j : p.x;
+          const uint32_t dst = bbase + (uint32_t)ch * WTC_BLK + (uint32_t)q * 128u +
+                               ((((j >> 1) ^ (uint32_t)(q & 3)) << 5) | ((j & 1) << 4));
+          cp_async16_zfill(dst, src, ok ? 16u : 0u);
+        }
       }
       cp_async_commit();
       if (st >= 1) {
@@ -506,14 +541,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
     fence_proxy_async();
     if (steps > 0) mbar_arrive(full_bar((steps - 1) % S));
 
-    // ---- epilogue: lane = out channel m; columns = (tap, c)
+    // ---- epilogue: lane = out channel m; columns = (tap, c); transposed through smem for coalesced stores
     if (steps > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-    const int m = mch0 + threadIdx.x;
-    const bool mok = m < p.Cm;
-    float* __restrict__ prow = p.part + ((long long)blockIdx.z * p.Cm + (mok ? m : 0)) * p.K;
+    const int r_own = warp * 32 + lane;
+    const int rsub = lane >> 3;
+    const uint32_t stg = smem_base;  // stage 0's G region (16 KB), idle now
+    float* __restrict__ pbase = p.part + (long long)blockIdx.z * p.Cm * p.K;
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
     const int ncols = p.TT * p.Nc;
     for (int cc = 0; cc < ncols; cc += 32) {
@@ -523,16 +559,28 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
+        for (int q = 0; q < 32; ++q) v[q] = 0u;
       }
-      if (mok) {
-        const int ti = cc / p.Nc, cin = cc - ti * p.Nc;
-        float* dstp = prow + (long long)(t0 + ti) * p.Cx + c0 + cin;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dstp + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                             __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      for (int q = 0; q < 8; ++q)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r_own * 128u +
+                                                                    (((uint32_t)q ^ (uint32_t)(r_own & 7)) << 4)),
+                     "r"(v[4 * q]), "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                     : "memory");
+      __syncwarp();
+      const int ti = cc / p.Nc, cin = cc - ti * p.Nc;
+      const long long colofs = (long long)(t0 + ti) * p.Cx + c0 + cin + 4 * j;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp * 32 + i * 4 + rsub;
+        const int m = mch0 + r;
+        float4 o;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                     : "r"(stg + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
+        if (m < p.Cm) *reinterpret_cast<float4*>(pbase + (long long)m * p.K + colofs) = o;
       }
+      __syncwarp();
     }
   } else if (warp == 4) {
     // =============================================================== G tile via TMA
@@ -609,7 +657,7 @@ size_t conv_wgrad_tc_workspace_bytes(const SgkConvDesc* d) {
   return (size_t)w.splits * e.O * e.I * e.k * e.k * sizeof(float);
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int O, int I, int k, int splits);
+int launch_wgrad_reduce(const float* part, float* dw, int O, int I, int k, int splits, cudaStream_t st);
 
 int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
@@ -650,10 +698,7 @@ int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* 
   dim3 grid((unsigned)((e.k * e.k / w.TT) * (e.I / w.Nc)), (unsigned)ceil_div(e.O, 128), (unsigned)w.splits);
   conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, map);
   SGK_LAUNCH_CHECK("conv_wgrad_tc_kernel");
-  long long total = (long long)e.O * e.I * e.k * e.k;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>((const float*)ws, dw, e.O, e.I, e.k, w.splits);
-  SGK_LAUNCH_CHECK("wgrad_reduce_kernel");
-  return SGK_OK;
+  return launch_wgrad_reduce((const float*)ws, dw, e.O, e.I, e.k, w.splits, st);
 }
 
 }  // namespace sgk
