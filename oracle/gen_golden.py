@@ -159,7 +159,80 @@ def main():
         blob["meta.steps"] = np.array(steps)
         np.savez_compressed(os.path.join(OUT, "fcgan_step_%s.npz" % tag), **blob)
         print("wrote fcgan_step", tag, blob["out.loss%d" % (steps - 1)])
+    step_fixtures()
+
+
+def step_fixtures():
+    """cgan and twostage_cycle optimize_parameters fixtures (cgan_model.py:210-225; twostage_cycle_model.py:412-438)."""
+    # ---- CGANModel: unet_128 G + 2 D's on cat(A, B), weighted L1
+    Model = R.load_model_class("cgan")
+    seed(200)
+    opt = R.cgan_opt(batchSize=1, fineSize=128, ngf=2, ndf=4, pool_size=0, weights=[2.0, 3.0], scale_factor=[1, 2],
+                     n_layers_D=[3, 2], lambda_D=[0.6, 0.4])
+    m = Model()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.initialize(opt)
+    blob = {}
+    blob.update(pack("sdG", m.netG.state_dict()))
+    for i, d in enumerate(m.netD):
+        blob.update(pack("sdD%d" % i, d.state_dict()))
+    steps = 2
+    for t in range(steps):
+        x = torch.rand(1, 3, 128, 128) * 2 - 1
+        m.set_input({"A": x, "A_paths": ["x"]})
+        m.optimize_parameters()
+        blob["in.real_A%d" % t] = m.real_A.detach().numpy().copy()
+        blob["in.real_B%d" % t] = m.real_B.detach().numpy().copy()
+        blob["out.loss%d" % t] = np.array([float(m.loss_G), float(m.loss_G_L1), float(m.loss_D_real), float(m.loss_D_fake)])
+        if t == 0:
+            blob["out.fake_B0"] = m.fake_B.detach().numpy().copy()
+    blob.update(pack("sdG_after", m.netG.state_dict()))
+    blob["meta.steps"] = np.array(steps)
+    np.savez_compressed(os.path.join(OUT, "cgan_step.npz"), **blob)
+    print("wrote cgan_step", blob["out.loss%d" % (steps - 1)])
+
+    # ---- TwoStageCycleModel: fcgan G1 -> bilinear x2 -> CRN G2, unet_128 F2, 2 D1's, 2 D2's
+    Model = R.load_model_class("twostage_cycle")
+    seed(300)
+    opt = R.twostage_opt(batchSize=1, fineSize=128, noiseSize1=1, noiseSize2=2, ngf1=4, ngf2=8, nff2=2, ndf1=4, ndf2=4,
+                         n_layers_G1=4, pool_size=0, scale_factor1=[1, 2], n_layers_D1=[3, 2], lambda_D1=[0.5, 0.4],
+                         scale_factor2=[1, 2], n_layers_D2=[3, 3], lambda_D2=[0.6, 0.4],
+                         GAN_losses_D2=["real_fake", "fake_fake"], GAN_losses_G2=["real_fake", "fake_fake"])
+    m = Model()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.initialize(opt)
+    blob = {}
+    for lab, net in (("G1", m.netG1), ("G2", m.netG2), ("F2", m.netF2)):
+        blob.update(pack("sd" + lab, net.state_dict()))
+    for i, d in enumerate(m.netD1):
+        blob.update(pack("sdD1_%d" % i, d.state_dict()))
+    for i, d in enumerate(m.netD2):
+        blob.update(pack("sdD2_%d" % i, d.state_dict()))
+    steps = 2
+    for t in range(steps):
+        x = torch.rand(1, 3, 128, 128) * 2 - 1
+        m.set_input({"A": x, "A_paths": ["x"]})
+        m.optimize_parameters()
+        blob["in.real_A%d" % t] = m.real_A.detach().numpy().copy()
+        blob["in.real_B%d" % t] = m.real_B.detach().numpy().copy()
+        blob["in.noise1_%d" % t] = m.noise1.detach().numpy().copy()
+        blob["in.noise2_%d" % t] = m.noise2.detach().numpy().copy()
+        blob["out.loss%d" % t] = np.array([float(v) for v in (m.loss_G, m.loss_G1_GAN, m.loss_G2_GAN, m.loss_G2_L1, m.loss_F2_CE,
+                                                               m.loss_G2_real_cycle, m.loss_G2_fake_cycle, m.loss_D1_real,
+                                                               m.loss_D1_fake, m.loss_D2_real, m.loss_D2_fake)])
+        if t == 0:
+            blob["out.fake_A0"] = m.fake_A.detach().numpy().copy()
+            blob["out.fake_B_from_fake_A0"] = m.fake_B_from_fake_A.detach().numpy().copy()
+            blob["out.recon_fake_A0"] = m.recon_fake_A.detach().numpy().copy()
+    blob["meta.steps"] = np.array(steps)
+    np.savez_compressed(os.path.join(OUT, "twostage_step.npz"), **blob)
+    print("wrote twostage_step", blob["out.loss%d" % (steps - 1)])
 
 
 if __name__ == "__main__":
+    if "--steps-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        R.load()
+        step_fixtures()
+        sys.exit(0)
     main()

@@ -394,3 +394,168 @@ def init_nlayer_discriminator(gen, input_nc=2, ndf=32, n_layers=3, scale_factor=
     idx += 3
     conv(idx, ndf * mult, 1)
     return sd
+
+
+# ----------------------------------------------------------------------------
+# shared helpers for the conditional / two-stage step restatements
+# ----------------------------------------------------------------------------
+def _prep_sd(sd, dtype, trainable=True):
+    out = {}
+    for k, v in sd.items():
+        t = v.detach().clone()
+        if t.is_floating_point():
+            t = t.to(dtype)
+            stat = k.endswith("running_mean") or k.endswith("running_var")
+            if trainable and not stat:
+                t.requires_grad_(True)
+        out[k] = t
+    return out
+
+
+def _model_params(sd):
+    return [v for k, v in sd.items() if k.startswith("model.") and v.requires_grad]
+
+
+def _all_params(sd):
+    return [v for v in sd.values() if v.is_floating_point() and v.requires_grad]
+
+
+def l1_weight_map(real_A, weights):
+    # cgan_model.py:197-206
+    if weights is None:
+        return None
+    a = (real_A.detach() + 1) / 2
+    w = torch.ones(a.shape[0], 1, a.shape[2], a.shape[3], dtype=a.dtype)
+    for i, wi in enumerate(weights):
+        w = w + a[:, i:i + 1] * (wi - 1.0)
+    return w
+
+
+# ----------------------------------------------------------------------------
+# CGANModel step  cgan_model.py:131-225
+# ----------------------------------------------------------------------------
+class CganStep:
+    def __init__(self, sd_G, sds_D, num_downs=7, n_layers_D=(3, 4), scale_factor=(1, 1), lambda_D=(0.5, 0.5), lambda_A=10.0,
+                 weights=None, no_lsgan=True, no_cgan=False, lr=2e-4, beta1=0.5, dtype=torch.float32):
+        self.sd_G = _prep_sd(sd_G, dtype)
+        self.sds_D = [_prep_sd(sd, dtype) for sd in sds_D]
+        self.num_downs, self.n_layers_D, self.scale_factor = num_downs, list(n_layers_D), list(scale_factor)
+        self.lambda_D, self.lambda_A, self.weights = list(lambda_D), lambda_A, weights
+        self.no_lsgan, self.no_cgan = no_lsgan, no_cgan
+        self.params_G = _all_params(self.sd_G)
+        self.params_D = [p for sd in self.sds_D for p in _model_params(sd)]
+        self.opt_G, self.opt_D = Adam(self.params_G, lr, beta1), Adam(self.params_D, lr, beta1)
+
+    def D(self, i, x):
+        return nlayer_discriminator(self.sds_D[i], x, self.n_layers_D[i], self.scale_factor[i], self.no_lsgan)
+
+    def step(self, real_A, real_B):
+        crit = lambda p, t: gan_loss(p, t, use_lsgan=not self.no_lsgan)
+        pair = (lambda a, b: b) if self.no_cgan else (lambda a, b: torch.cat((a, b), 1))
+        nD = len(self.sds_D)
+        fake_B = unet_generator(self.sd_G, real_A, self.num_downs)
+        self.fake_B = fake_B
+        self.opt_D.zero_grad()
+        for sd in self.sds_D:
+            for v in sd.values():
+                v.grad = None
+        fake = pair(real_A, fake_B).detach()
+        self.loss_D_fake = sum(crit(self.D(i, fake), False) for i in range(nD))
+        self.loss_D_real = sum(crit(self.D(i, pair(real_A, real_B)), True) for i in range(nD))
+        ((self.loss_D_fake + self.loss_D_real) * 0.5).backward()
+        self.grads_D = [p.grad.clone() for p in self.params_D]
+        self.opt_D.step()
+        self.opt_G.zero_grad()
+        fake = pair(real_A, fake_B)
+        loss_G = sum(crit(self.D(i, fake), True) * self.lambda_D[i] for i in range(nD))
+        self.loss_G_L1 = weighted_l1(fake_B, real_B, l1_weight_map(real_A, self.weights)) * self.lambda_A
+        self.loss_G = loss_G + self.loss_G_L1
+        self.loss_G.backward()
+        self.grads_G = [p.grad.clone() for p in self.params_G]
+        self.opt_G.step()
+        return [float(self.loss_G.detach()), float(self.loss_G_L1.detach()), float(self.loss_D_real.detach()),
+                float(self.loss_D_fake.detach())]
+
+
+# ----------------------------------------------------------------------------
+# TwoStageCycleModel step  twostage_cycle_model.py:193-438 (binary GAN recipe)
+# ----------------------------------------------------------------------------
+class TwoStageStep:
+    def __init__(self, sd_G1, sd_G2, sd_F2, sds_D1, sds_D2, cfg, dtype=torch.float32):
+        """cfg: dict with n_layers_G1, use_fcn1, crn_mode, crn_blocks, f2_downs, n_layers_D1, scale_factor1, lambda_D1,
+        n_layers_D2, scale_factor2, lambda_D2, GAN_losses_D2, GAN_losses_G2, lambda_A, lambda_B, lambda_A_cycle,
+        lambda_fake_cycle, lr1, lr2, beta1, sc (transform scale), weights."""
+        self.c = cfg
+        self.sd_G1, self.sd_G2, self.sd_F2 = _prep_sd(sd_G1, dtype), _prep_sd(sd_G2, dtype), _prep_sd(sd_F2, dtype)
+        self.sds_D1 = [_prep_sd(sd, dtype) for sd in sds_D1]
+        self.sds_D2 = [_prep_sd(sd, dtype) for sd in sds_D2]
+        self.params_G1, self.params_G2, self.params_F2 = _all_params(self.sd_G1), _all_params(self.sd_G2), _all_params(self.sd_F2)
+        self.params_D1 = [p for sd in self.sds_D1 for p in _model_params(sd)]
+        self.params_D2 = [p for sd in self.sds_D2 for p in _model_params(sd)]
+        b = cfg.get("beta1", 0.5)
+        self.opt_G1, self.opt_G2, self.opt_F2 = Adam(self.params_G1, cfg["lr1"], b), Adam(self.params_G2, cfg["lr2"], b), Adam(self.params_F2, cfg["lr2"], b)
+        self.opt_D1, self.opt_D2 = Adam(self.params_D1, cfg["lr1"], b), Adam(self.params_D2, cfg["lr2"], b)
+
+    def step(self, real_A, real_B, noise1, noise2):
+        c = self.c
+        G1 = lambda z: fcgan_generator(self.sd_G1, z, c["n_layers_G1"], c["use_fcn1"])
+        G2 = lambda l: crn_generator(self.sd_G2, l, noise2, c["crn_mode"], c["crn_blocks"])
+        F2 = lambda x: unet_generator(self.sd_F2, x, c["f2_downs"])
+        D1 = lambda i, x: nlayer_discriminator(self.sds_D1[i], x, c["n_layers_D1"][i], c["scale_factor1"][i], True)
+        D2 = lambda i, x: nlayer_discriminator(self.sds_D2[i], x, c["n_layers_D2"][i], c["scale_factor2"][i], True)
+        up = lambda x: transform_up(x, c["sc"])
+        down = lambda x: transform_down(x, c["sc"])
+        crit = lambda p, t: gan_loss(p, t, use_lsgan=False)
+        # forward (:193-211)
+        fake_A = G1(noise1)
+        fake_A_from_real_B = F2(real_B)
+        fake_B_from_real_A = G2(real_A)
+        fake_B_from_fake_A = G2(up(fake_A))
+        recon_real_A = F2(fake_B_from_real_A)
+        recon_fake_A = F2(fake_B_from_fake_A)
+        self.fake_A, self.fake_B_from_fake_A, self.recon_fake_A = fake_A, fake_B_from_fake_A, recon_fake_A
+        # D1 (:245-262)
+        self.opt_D1.zero_grad()
+        l_f = sum(crit(D1(i, fake_A.detach()), False) for i in range(len(self.sds_D1)))
+        l_r = sum(crit(D1(i, down(real_A)), True) for i in range(len(self.sds_D1)))
+        self.loss_D1_fake, self.loss_D1_real = l_f, l_r
+        ((l_f + l_r) * 0.5).backward()
+        self.opt_D1.step()
+        # D2 (:264-300)
+        self.opt_D2.zero_grad()
+        l_f, npairs = 0, 0
+        if "real_fake" in c["GAN_losses_D2"]:
+            fake = torch.cat([real_A, fake_B_from_real_A], 1).detach(); npairs += 1
+            l_f = l_f + sum(crit(D2(i, fake), False) for i in range(len(self.sds_D2)))
+        if "fake_fake" in c["GAN_losses_D2"]:
+            fake = torch.cat([up(fake_A), fake_B_from_fake_A], 1).detach(); npairs += 1
+            l_f = l_f + sum(crit(D2(i, fake), False) for i in range(len(self.sds_D2)))
+        l_f = l_f / npairs
+        l_r = sum(crit(D2(i, torch.cat([real_A, real_B], 1)), True) for i in range(len(self.sds_D2)))
+        self.loss_D2_fake, self.loss_D2_real = l_f, l_r
+        ((l_f + l_r) * 0.5).backward()
+        self.opt_D2.step()
+        # G (:337-410)
+        for o in (self.opt_G1, self.opt_G2, self.opt_F2):
+            o.zero_grad()
+        l_g1 = sum(crit(D1(i, fake_A), True) * c["lambda_D1"][i] for i in range(len(self.sds_D1)))
+        l_g2, npairs = 0, 0
+        if "real_fake" in c["GAN_losses_G2"]:
+            fake = torch.cat([real_A, fake_B_from_real_A], 1); npairs += 1
+            l_g2 = l_g2 + sum(crit(D2(i, fake), True) * c["lambda_D2"][i] for i in range(len(self.sds_D2)))
+        if "fake_fake" in c["GAN_losses_G2"]:
+            fake = torch.cat([up(fake_A), fake_B_from_fake_A], 1); npairs += 1
+            l_g2 = l_g2 + sum(crit(D2(i, fake), True) * c["lambda_D2"][i] for i in range(len(self.sds_D2)))
+        l_l1 = weighted_l1(fake_B_from_real_A, real_B, l1_weight_map(real_A, c.get("weights"))) if "real_fake" in c["GAN_losses_G2"] else 0
+        l_ce = cycle_bce(fake_A_from_real_B, real_A)
+        l_rc = cycle_bce(recon_real_A, real_A)
+        l_fc = cycle_bce(recon_fake_A, up(fake_A.detach()))
+        loss_G = l_g1 + l_g2 / npairs + l_l1 * c["lambda_A"] + l_ce * c["lambda_B"] + l_rc * c["lambda_A_cycle"] \
+            + l_fc * c["lambda_A_cycle"] * c["lambda_fake_cycle"]
+        loss_G.backward()
+        self.grads_G = [p.grad.clone() for p in self.params_G1 + self.params_G2 + self.params_F2]
+        for o in (self.opt_G1, self.opt_G2, self.opt_F2):
+            o.step()
+        f = lambda v: float(v.detach()) if torch.is_tensor(v) else float(v)
+        return [f(v) for v in (loss_G, l_g1, l_g2, l_l1, l_ce, l_rc, l_fc, self.loss_D1_real, self.loss_D1_fake,
+                               self.loss_D2_real, self.loss_D2_fake)]

@@ -94,3 +94,37 @@ def fcgan_opt(**kw):
     d.update(kw)
     d["scale_factor"] = [sf(int(s)) for s in d["scale_factor"]]
     return argparse.Namespace(**d)
+
+
+def cgan_opt(**kw):
+    """Fields CGANModel.initialize reads (cgan_model.py:18-115) on top of the fcgan ones."""
+    d = dict(which_channel="rg_b", which_model_netG="unet_128", ngf=64, ndf=64, scale_factor=[1, 1], lambda_D=[0.5, 0.5],
+             n_layers_D=[3, 4], transform_1to2="none", n_layers_G_skip=-1, no_cgan=False, weights=None,
+             dataset_mode="single", lambda_A=10.0, which_direction="AtoB", noiseSize=8)
+    d.update(kw)
+    return fcgan_opt(**d)
+
+
+def twostage_opt(**kw):
+    """Fields TwoStageCycleModel.initialize reads (twostage_cycle_model.py:18-177); README.md:18 recipe, reduced widths via kw."""
+    d = dict(isTrain=True, gpu_ids=[], checkpoints_dir="/tmp/sgk_ckpt", name="oracle", pretrained_model_dir="",
+             which_channel="rg_b", batchSize=1, input_nc=2, output_nc=1, fineSize=512, norm="instance",
+             noise_nc1=8, noiseSize1=4, noise_nc2=8, noiseSize2=8, ngf1=32, ngf2=64, nff2=32, ndf1=32, ndf2=64,
+             which_model_netG1="fcgan", which_model_netG2="crn", which_model_netF2="unet_128",
+             which_model_netD1="n_layers", which_model_netD2="n_layers", which_model_netD="n_layers",
+             n_layers_G1=5, n_layers_G2=5, n_layers_F2=5, no_dropout1=True, no_dropout2=True, use_residual2=False,
+             add_gaussian_noise=False, gaussian_sigma=0.1, upsample_mode1="convt", upsample_mode2="bilinear",
+             n_layers_CRN_block1=1, n_layers_CRN_block2=2, no_share_label_block_weights1=False,
+             no_share_label_block_weights2=False, transform_1to2="bilinear_2", scale_factor1=[1, 2], lambda_D1=[0.5, 0.4],
+             n_layers_D1=[3, 3], scale_factor2=[1, 1, 2, 2], lambda_D2=[0.3, 0.3, 0.2, 0.2], n_layers_D2=[3, 4, 3, 4],
+             no_lsgan1=True, no_lsgan2=True, no_cgan=False, use_multi_class_GAN=False, use_fixed_noise1=False,
+             noise_pool_size=100, sequential_train=False, which_model_to_load=[""], which_epoch_sequential="seq",
+             continue_train=False, which_epoch="latest", pool_size=50, lr=2e-4, lr1=2e-4, lr2=2e-4, beta1=0.5,
+             which_direction="AtoB", dataset_mode="single", n_update_D1=1, n_update_D2=1, n_update_G=1,
+             no_logD_trick=False, detach_G1_from_G2_x=False, detach_G1_from_G2_y=False, GAN_losses_D2=["real_fake"],
+             GAN_losses_G2=["real_fake"], weights=None, lambda_A=10.0, lambda_B=10.0, lambda_A_cycle=5.0,
+             lambda_fake_cycle=1.0, niter_decay=100)
+    d.update(kw)
+    d["scale_factor1"] = [sf(int(s)) for s in d["scale_factor1"]]
+    d["scale_factor2"] = [sf(int(s)) for s in d["scale_factor2"]]
+    return argparse.Namespace(**d)

@@ -1,0 +1,93 @@
+"""Shared plumbing of the step drivers (reference: models/base_model.py:8-64): device handling, the
+`which_channel` parser, reference-compatible '<epoch>_net_<label>.pth' checkpoints, linear lr decay."""
+import os
+
+import torch
+
+from . import networks, ops
+
+
+class BaseModel(object):
+    def name(self):
+        return 'BaseModel'
+
+    def initialize(self, opt):
+        self.opt = opt
+        self.gpu_ids = opt.gpu_ids
+        self.isTrain = opt.isTrain
+        if not self.gpu_ids or not torch.cuda.is_available():
+            raise RuntimeError("supervised-gan_b200 runs on CUDA only: pass gpu_ids=[<device>] (no CPU fallback)")
+        self.device = torch.device("cuda", self.gpu_ids[0])
+        self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
+        self.model_dir = getattr(opt, "pretrained_model_dir", "")
+        self.grad_sync = None  # data-parallel hook: callable(list_of_params, tag) between backward and step
+        self.skip_unused_grads = getattr(opt, "skip_unused_grads", True)
+
+    @staticmethod
+    def parse_channels(which_channel):
+        idx_dict = {'r': 0, 'g': 1, 'b': 2}
+        return [torch.tensor([idx_dict[c] for c in s], dtype=torch.long) for s in which_channel.split('_')]
+
+    def make_transform(self, spec):
+        """--transform_1to2 'bilinear_<sc>' (cgan_model.py:51-57; twostage_cycle_model.py:64-70)."""
+        if 'bilinear' in spec:
+            sc = int(spec.split('_')[1])
+            return networks.Upsample(scale_factor=sc, mode='bilinear'), networks.AvgPool2d(kernel_size=sc, stride=sc)
+        return (lambda x: x), (lambda x: x)
+
+    def l1_weight_map(self, real_A):
+        """weight = 1 + sum_i ((real_A_i + 1) / 2) (weights_i - 1)  (cgan_model.py:197-206)."""
+        if self.opt.weights is None:
+            return None
+        a = (real_A.detach() + 1) / 2
+        weight = torch.ones(a.shape[0], 1, a.shape[2], a.shape[3], device=a.device)
+        for i in range(len(self.opt.weights)):
+            weight = weight + a.narrow(1, i, 1) * (self.opt.weights[i] - 1.0)
+        return weight
+
+    def _draw(self, buf, shape):
+        if buf is None or tuple(buf.shape) != tuple(shape):
+            buf = torch.empty(shape, device=self.device)
+        return buf.normal_(0, 1)
+
+    class frozen(object):
+        """Context: parameters of nets whose gradients nobody consumes in this phase do not require grad."""
+
+        def __init__(self, params, enabled):
+            self.params, self.enabled = params, enabled
+
+        def __enter__(self):
+            if self.enabled:
+                for p in self.params:
+                    p.requires_grad_(False)
+
+        def __exit__(self, *a):
+            if self.enabled:
+                for p in self.params:
+                    p.requires_grad_(True)
+
+    def _step(self, optimizer, params, tag):
+        if self.grad_sync is not None:
+            self.grad_sync(params, tag)
+        optimizer.step()
+
+    # ------------------------------------------------------------------ checkpoints (base_model.py:44-61)
+    def save_network(self, network, network_label, epoch_label, gpu_ids=[], model_dir=''):
+        save_filename = '%s_net_%s.pth' % (epoch_label, network_label)
+        save_path = os.path.join(model_dir or self.save_dir, save_filename)
+        os.makedirs(os.path.dirname(save_path), exist_ok=True)
+        torch.save({k: v.detach().cpu() for k, v in network.state_dict().items()}, save_path)
+
+    def load_network(self, network, network_label, epoch_label, model_dir=''):
+        save_filename = '%s_net_%s.pth' % (epoch_label, network_label)
+        save_path = os.path.join(model_dir or self.save_dir, save_filename)
+        network.load_state_dict(torch.load(save_path, map_location=self.device))
+        ops.bump_weights_epoch()
+
+    def _decay(self, optimizers, old, base):
+        lr = old - base / self.opt.niter_decay
+        for o in optimizers:
+            for g in o.param_groups:
+                g['lr'] = lr
+        print('update learning rate: %f -> %f' % (old, lr))
+        return lr
