@@ -28,6 +28,7 @@ struct GatherPhase {
   int ry0, rx0;      // raw-weight tap of a=0 / b=0 ...
   int rstep;         // ... and its step per tap (may be negative)
   long long w_off;   // element offset of this phase in the packed weight
+  int kstride;       // row stride of the packed weight: K = ta*tb*Cg rounded up to 32 (zero padded)
   int m_tile_begin;  // first M tile of this phase in the launch grid (filled by the launcher)
 };
 
@@ -91,7 +92,8 @@ inline GatherPlan make_gather_plan(const SgkConvDesc& d, int op) {
     GatherPhase& p = g.ph[0];
     p.Hp = e.Hs; p.Wp = e.Ws; p.ta = e.k; p.tb = e.k; p.is = e.s; p.ioy = -e.p; p.iox = -e.p;
     p.os = 1; p.ooy = 0; p.oox = 0; p.ry0 = 0; p.rx0 = 0; p.rstep = 1; p.w_off = 0; p.m_tile_begin = 0;
-    g.packed_elems = (long long)e.O * e.k * e.k * e.I;
+    p.kstride = (e.k * e.k * e.I + 31) / 32 * 32;
+    g.packed_elems = (long long)e.O * p.kstride;
   } else {
     g.Hi = e.Hs; g.Wi = e.Ws; g.Cg = e.O;
     g.Ho = e.Hb; g.Wo = e.Wb; g.Co = e.I;
@@ -111,7 +113,8 @@ inline GatherPlan make_gather_plan(const SgkConvDesc& d, int op) {
         // tap a reads raw tap r = r0 + s*(ta-1-a)
         p.ry0 = r0y + e.s * (p.ta - 1); p.rx0 = r0x + e.s * (p.tb - 1); p.rstep = -e.s;
         p.w_off = off;
-        off += (long long)e.I * p.ta * p.tb * e.O;
+        p.kstride = (p.ta * p.tb * e.O + 31) / 32 * 32;
+        off += (long long)e.I * p.kstride;
         g.ph[g.nphase++] = p;
       }
     g.packed_elems = off;

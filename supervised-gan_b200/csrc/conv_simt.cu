@@ -31,13 +31,16 @@ __global__ void pack_weight_kernel(const __grid_constant__ PackParams p) {
     if (i < p.nphase && idx >= p.ph[i].w_off) ph = i;
   const GatherPhase& P = p.ph[ph];
   long long local = idx - P.w_off;
-  int Cg = p.transposed_type ? p.O : p.I;  // gathered channel count (innermost)
-  int c = (int)(local % Cg);
-  long long t = local / Cg;
-  int b = (int)(t % P.tb);
-  t /= P.tb;
-  int a = (int)(t % P.ta);
-  int n = (int)(t / P.ta);
+  const int Cg = p.transposed_type ? p.O : p.I;  // gathered channel count (innermost)
+  const int n = (int)(local / P.kstride);
+  const int kk = (int)(local - (long long)n * P.kstride);
+  if (kk >= P.ta * P.tb * Cg) {  // zero padding of the K dimension up to a multiple of 32
+    p.packed[idx] = 0.f;
+    return;
+  }
+  const int c = kk % Cg;
+  const int t = kk / Cg;
+  const int b = t % P.tb, a = t / P.tb;
   int ry = P.ry0 + P.rstep * a, rx = P.rx0 + P.rstep * b;
   int o = p.transposed_type ? c : n;
   int i = p.transposed_type ? n : c;
@@ -147,11 +150,11 @@ __global__ void __launch_bounds__(F_THREADS) gather_gemm_f(const __grid_constant
       int k = kbase + bkq;
       if (VEC) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bco < p.Co && k < K) v = __ldg(reinterpret_cast<const float4*>(W + (long long)bco * K + k));
+        if (bco < p.Co && k < K) v = __ldg(reinterpret_cast<const float4*>(W + (long long)bco * P.kstride + k));
         breg[0] = v.x; breg[1] = v.y; breg[2] = v.z; breg[3] = v.w;
       } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) breg[i] = (bco < p.Co && k + i < K) ? __ldg(W + (long long)bco * K + k + i) : 0.f;
+        for (int i = 0; i < 4; ++i) breg[i] = (bco < p.Co && k + i < K) ? __ldg(W + (long long)bco * P.kstride + k + i) : 0.f;
       }
     }
   };
@@ -260,7 +263,6 @@ __global__ void __launch_bounds__(256) gather_thin_out(const __grid_constant__ F
   int rem = (int)(m - (long long)n * HWp);
   int oy = rem / P.Wp, ox = rem - oy * P.Wp;
   const int iy0 = oy * P.is + P.ioy, ix0 = ox * P.is + P.iox;
-  const int K = P.ta * P.tb * p.Cg;
   const float* __restrict__ W = p.w + P.w_off;
   const float* __restrict__ in_n = p.in + (long long)n * p.Hi * p.Wi * p.Cg;
   float acc[CO];
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(256) gather_thin_out(const __grid_constant__ F
 #pragma unroll
             for (int j = 0; j < CO; ++j) {
               if (j < p.Co) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)j * K + kofs + c));
+                const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)j * P.kstride + kofs + c));
                 acc[j] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[j]))));
               }
             }
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(256) gather_thin_out(const __grid_constant__ F
             const float v = __ldg(px + c);
 #pragma unroll
             for (int j = 0; j < CO; ++j)
-              if (j < p.Co) acc[j] = fmaf(v, __ldg(W + (long long)j * K + kofs + c), acc[j]);
+              if (j < p.Co) acc[j] = fmaf(v, __ldg(W + (long long)j * P.kstride + kofs + c), acc[j]);
           }
         }
       }

@@ -54,6 +54,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// 4- and 8-byte variants (thin-channel gathers); .ca is the only cache operator allowed below 16 bytes
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -140,6 +147,7 @@ struct TcParams {
   int nphase;
   GatherPhase ph[4];
   int BN, stages, tmem_cols;
+  int cs;  // 0: Cg % 32 == 0 (one tap x 32 channels per k-block); 4/8/16: thin Cg, k-block = 32 flattened (tap, c) slots copied cs bytes at a time
 };
 
 constexpr int TC_BM = 128;
@@ -170,8 +178,8 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
   const long long M = (long long)p.N * HWp;
   const long long m0 = (long long)(blockIdx.x - P.m_tile_begin) * TC_BM;
   const int n0 = blockIdx.y * p.BN;
-  const int cchunks = p.Cg >> 5;
-  const int KB = P.ta * P.tb * cchunks;
+  const int Kreal = P.ta * P.tb * p.Cg;
+  const int KB = P.kstride >> 5;
 
   // per-row tables (written once): gather origin and output address of each of the 128 tile rows
   const uint32_t rowinfo = tmem_slot + 8u;            // int4 {image n, iy0, ix0, valid}
@@ -212,20 +220,46 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
     const uint32_t j = (uint32_t)(lane & 7);   // 16-B chunk of the row
     const int rsub = lane >> 3;                // row within the group of 4 rows one instruction covers
     int a = 0, b = 0, c0 = 0;
+    // thin-channel mode: this lane always serves the same slot of the 128-B row
+    const int spr = p.cs ? 128 / p.cs : 8;       // slots per row
+    const int rpi = 32 / spr;                    // rows covered by one warp-wide instruction
+    const int slot = lane % spr, tsub = lane / spr;
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % S;
       mbar_wait(empty_bar(s), (uint32_t)(((kb / S) & 1) ^ 1));
       const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
+      if (p.cs == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = warp * 32 + i * 4 + rsub;
-        int n, iy, ix, ok;
-        asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(n), "=r"(iy), "=r"(ix), "=r"(ok) : "r"(rowinfo + 16u * r));
-        iy += a;
-        ix += b;
-        const bool good = ok && (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
-        const float* src = good ? p.in + (((long long)n * p.Hi + iy) * p.Wi + ix) * p.Cg + c0 + 4 * j : p.in;
-        cp_async16_zfill(abase + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4), src, good ? 16u : 0u);
+        for (int i = 0; i < 8; ++i) {
+          const int r = warp * 32 + i * 4 + rsub;
+          int n, iy, ix, ok;
+          asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(n), "=r"(iy), "=r"(ix), "=r"(ok) : "r"(rowinfo + 16u * r));
+          iy += a;
+          ix += b;
+          const bool good = ok && (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
+          const float* src = good ? p.in + (((long long)n * p.Hi + iy) * p.Wi + ix) * p.Cg + c0 + 4 * j : p.in;
+          cp_async16_zfill(abase + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4), src, good ? 16u : 0u);
+        }
+      } else {
+        const int k = kb * 32 + slot * (p.cs >> 2);   // first flattened (tap, channel) index of this slot
+        const bool kok = k < Kreal;
+        const int tap = kok ? k / p.Cg : 0;
+        const int cch = kok ? k - tap * p.Cg : 0;
+        const int ta_ = tap / P.tb, tb_ = tap - ta_ * P.tb;
+        const uint32_t boff = (uint32_t)(slot * p.cs);
+        for (int i = 0; i < 32 / rpi; ++i) {
+          const int r = warp * 32 + i * rpi + tsub;
+          int n, iy, ix, ok;
+          asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(n), "=r"(iy), "=r"(ix), "=r"(ok) : "r"(rowinfo + 16u * r));
+          iy += ta_;
+          ix += tb_;
+          const bool good = kok && ok && (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
+          const float* src = good ? p.in + (((long long)n * p.Hi + iy) * p.Wi + ix) * p.Cg + cch : p.in;
+          const uint32_t dst = abase + (uint32_t)r * 128u + ((((boff >> 4) ^ (uint32_t)(r & 7)) << 4) | (boff & 15u));
+          if (p.cs == 16) cp_async16_zfill(dst, src, good ? 16u : 0u);
+          else if (p.cs == 8) cp_async8_zfill(dst, src, good ? 8u : 0u);
+          else cp_async4_zfill(dst, src, good ? 4u : 0u);
+        }
       }
       cp_async_commit();
       if (kb >= LAG) {
@@ -234,7 +268,7 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
         mbar_arrive(full_bar((kb - LAG) % S));
       }
       c0 += 32;
-      if (c0 == p.Cg) {
+      if (c0 >= p.Cg) {
         c0 = 0;
         if (++b == P.tb) { b = 0; ++a; }
       }
@@ -253,14 +287,24 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
       uint32_t v[32];
       tmem_ld32(lane_addr + (uint32_t)cc, v);
       tmem_ld_wait();
+      const int ncol = min(32, p.Co - n0 - cc);   // valid output channels in this 32-column chunk (thin Cout: < 32)
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cc + 4 * q));
-        const float o0 = act_apply(__uint_as_float(v[4 * q + 0]) + bv.x, p.act, p.slope);
-        const float o1 = act_apply(__uint_as_float(v[4 * q + 1]) + bv.y, p.act, p.slope);
-        const float o2 = act_apply(__uint_as_float(v[4 * q + 2]) + bv.z, p.act, p.slope);
-        const float o3 = act_apply(__uint_as_float(v[4 * q + 3]) + bv.w, p.act, p.slope);
+        float bvv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias != nullptr) {
+          if (4 * q + 3 < ncol) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cc + 4 * q));
+            bvv[0] = bv.x; bvv[1] = bv.y; bvv[2] = bv.z; bvv[3] = bv.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (4 * q + e < ncol) bvv[e] = __ldg(p.bias + n0 + cc + 4 * q + e);
+          }
+        }
+        const float o0 = act_apply(__uint_as_float(v[4 * q + 0]) + bvv[0], p.act, p.slope);
+        const float o1 = act_apply(__uint_as_float(v[4 * q + 1]) + bvv[1], p.act, p.slope);
+        const float o2 = act_apply(__uint_as_float(v[4 * q + 2]) + bvv[2], p.act, p.slope);
+        const float o3 = act_apply(__uint_as_float(v[4 * q + 3]) + bvv[3], p.act, p.slope);
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r_own * 128u +
                                                                     (((uint32_t)q ^ (uint32_t)(r_own & 7)) << 4)),
                      "f"(o0), "f"(o1), "f"(o2), "f"(o3)
@@ -278,7 +322,17 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
                      : "r"(stg + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
-        if (ok) *reinterpret_cast<float4*>(p.out + oofs + n0 + cc + 4 * j) = o;
+        if (ok) {
+          float* dstp = p.out + oofs + n0 + cc + 4 * j;
+          if ((int)(4 * j) + 3 < ncol && (p.Co & 3) == 0) {
+            *reinterpret_cast<float4*>(dstp) = o;
+          } else {
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if ((int)(4 * j) + e < ncol) dstp[e] = ov[e];
+          }
+        }
       }
       __syncwarp();
     }
@@ -347,9 +401,23 @@ static int pick_bn(int Co) {
 int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, const float* w, const float* bias, float* out,
                 int act, float slope, cudaStream_t st) {
   if (d->precision != SGK_TF32) return SGK_EUNSUPPORTED;  // bf16 operands: not built yet
-  if ((g.Cg % 32) != 0 || (g.Co % 32) != 0) return SGK_EUNSUPPORTED;  // thin-channel layers: CUDA-core path
-  const int BN = pick_bn(g.Co);
-  if (BN == 0) return SGK_EUNSUPPORTED;
+  // Thin-channel problems (Cin < 32 or Cout <= 16) are HBM/issue-bound; measured on B200 the CUDA-core thin kernels
+  // beat the tensor-core tile for them (profiles/), so they are only routed here when SGK_TC_THIN=1.
+  static const bool tc_thin = getenv("SGK_TC_THIN") != nullptr && atoi(getenv("SGK_TC_THIN")) != 0;
+  if (!tc_thin && ((g.Cg % 32) != 0 || (g.Co % 32) != 0)) return SGK_EUNSUPPORTED;
+  // N tile: a divisor of Cout in {256,128,64,32}, or one 16-wide tile for thin outputs (Cout <= 16: images, logits)
+  int BN = pick_bn(g.Co);
+  if (BN == 0) {
+    if (g.Co > 16) return SGK_EUNSUPPORTED;
+    BN = 16;
+  }
+  // K blocks: 32 channels of one tap, or -- thin inputs -- 32 flattened (tap, channel) slots
+  int cs = 0;
+  if ((g.Cg % 32) != 0) {
+    if (g.Cg > 32) return SGK_EUNSUPPORTED;
+    cs = (g.Cg % 4 == 0) ? 16 : ((g.Cg % 2 == 0) ? 8 : 4);
+    if (32 % g.Cg != 0 && cs != 4) cs = 4;   // slots must not straddle taps unless they are single elements
+  }
   for (int i = 0; i < g.nphase; ++i)
     if (g.ph[i].ta * g.ph[i].tb == 0) return SGK_EUNSUPPORTED;
   EncodeTiledFn encode = get_encode_tiled();
@@ -362,6 +430,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   p.act = act; p.slope = slope; p.nphase = g.nphase;
   p.BN = BN;
   p.tmem_cols = BN < 32 ? 32 : BN;
+  p.cs = cs;
   const uint32_t stage_bytes = TC_A_BYTES + BN * 128;
   int stages = (int)(98304 / stage_bytes);
   if (stages > 4) stages = 4;
@@ -372,7 +441,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
     p.ph[i] = g.ph[i];
     p.ph[i].m_tile_begin = (int)tiles;
     tiles += ceil_div64((long long)g.N * g.ph[i].Hp * g.ph[i].Wp, TC_BM);
-    const long long K = (long long)g.ph[i].ta * g.ph[i].tb * g.Cg;
+    const long long K = (long long)g.ph[i].kstride;   // zero-padded row length
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)g.Co};
     cuuint64_t gstr[1] = {(cuuint64_t)K * sizeof(float)};
     cuuint32_t box[2] = {32u, (cuuint32_t)BN};
@@ -386,7 +455,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   if (tiles > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return SGK_EUNSUPPORTED; }
   const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 2) + 128 * 24 + 1024;
   static bool attr_done[2] = {false, false};
-  dim3 grid((unsigned)tiles, (unsigned)(g.Co / BN));
+  dim3 grid((unsigned)tiles, (unsigned)ceil_div(g.Co, BN));
   if (stages == 2) {
     if (!attr_done[0]) {
       cudaError_t e = cudaFuncSetAttribute(conv_gather_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
@@ -442,7 +511,8 @@ struct WTcParams {
   int N, Hg, Wg, Cm, Hx, Wx, Cx, k, s, off, K;
   long long P, p_per_split;
   int TT, Nc, tmem_cols;
-  int variant;
+  int cs;     // 0: Cx % 32 == 0; else thin X: columns are the flattened (tap, c) index, copied cs bytes at a time
+  int Kflat;  // k*k*Cx
 };
 constexpr int WTC_P = 32;                       // pixels per stage
 constexpr int WTC_BLK = WTC_P * 128;            // one 32-channel block of a stage: 4096 B
@@ -465,9 +535,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
   const uint32_t tmem_slot = tmem_full_bar + 8u;
 
   // column tile: taps [t0, t0+TT) x channels [c0, c0+Nc)
-  const int ctiles = p.Cx / p.Nc;
-  const int t0 = ((int)blockIdx.x / ctiles) * p.TT;
-  const int c0 = ((int)blockIdx.x % ctiles) * p.Nc;
+  const int ctiles = p.cs ? 1 : p.Cx / p.Nc;
+  const int t0 = p.cs ? 0 : ((int)blockIdx.x / ctiles) * p.TT;
+  const int c0 = p.cs ? 0 : ((int)blockIdx.x % ctiles) * p.Nc;
   const int mch0 = blockIdx.y * 128;
   const long long pbeg = (long long)blockIdx.z * p.p_per_split;
   long long pend = pbeg + p.p_per_split;
@@ -491,43 +561,88 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
 
   if (warp < 4) {
     // =============================================================== X gather producers
-    // 8 lanes copy the 8 chunks of one 128-B (pixel, tap, channel-group) row: every cp.async instruction covers
-    // 4 rows = 4 x 128-B lines.  Thread t serves rows q = (t>>3) and (t>>3)+16 of every chunk.
-    const uint32_t j = (uint32_t)(threadIdx.x & 7);
-    const int grp = threadIdx.x >> 3;  // 0..15
+    // Per 32-pixel stage, threads 0..31 decode the pixels into a smem table; then 8 lanes (fat mode) copy the 8 chunks
+    // of one 128-B (pixel, tap, channel-group) row, so every cp.async instruction covers 4 rows = 4 x 128-B lines.
+    const uint32_t ptab = tmem_slot + 8u;  // [S][32] int4 {n, oy, ox, valid}
     const int HWg = p.Hg * p.Wg;
     const int nchunks = p.TT * ncg;
+    const int spr = p.cs ? 128 / p.cs : 8;          // lanes (slots) per 128-B row
+    const int rpp = 128 / spr;                      // rows served per pass of the 128 producer threads
+    const int slot = threadIdx.x % spr, rr = threadIdx.x / spr;
     for (int st = 0; st < steps; ++st) {
       const int s = st % S;
       mbar_wait(empty_bar(s), (uint32_t)(((st / S) & 1) ^ 1));
-      int pn[2], poy[2], pox[2];
-      bool pok[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const long long pix = pbeg + (long long)st * WTC_P + grp + 16 * h;
-        pok[h] = pix < pend;
-        pn[h] = 0; poy[h] = 0; pox[h] = 0;
-        if (pok[h]) {
-          pn[h] = (int)(pix / HWg);
-          int rem = (int)(pix - (long long)pn[h] * HWg);
-          poy[h] = rem / p.Wg;
-          pox[h] = rem - poy[h] * p.Wg;
-        }
-      }
       const uint32_t bbase = smem_base + (uint32_t)s * stage_bytes + WTC_A_BYTES;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int ti = ch / ncg, cg = ch - ti * ncg;
-        const int tap = t0 + ti;
-        const int a = tap / p.k, b = tap - a * p.k;
+      if (p.cs == 0) {
+        // fat mode: thread t serves rows q = (t>>3) and (t>>3)+16 of every chunk; decode them in registers
+        const int grp = threadIdx.x >> 3;
+        int pn[2], piy[2], pix_[2];
+        bool pok[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int q = grp + 16 * h;
-          const int iy = poy[h] * p.s + a + p.off, ix = pox[h] * p.s + b + p.off;
-          const bool ok = pok[h] && (unsigned)iy < (unsigned)p.Hx && (unsigned)ix < (unsigned)p.Wx;
-          const float* src = ok ? p.x + (((long long)pn[h] * p.Hx + iy) * p.Wx + ix) * p.Cx + c0 + cg * 32 + 4 * j : p.x;
-          const uint32_t dst = bbase + (uint32_t)ch * WTC_BLK + (uint32_t)q * 128u +
-                               ((((j >> 1) ^ (uint32_t)(q & 3)) << 5) | ((j & 1) << 4));
-          cp_async16_zfill(dst, src, ok ? 16u : 0u);
+          const long long pix = pbeg + (long long)st * WTC_P + grp + 16 * h;
+          pok[h] = pix < pend;
+          pn[h] = 0; piy[h] = 0; pix_[h] = 0;
+          if (pok[h]) {
+            pn[h] = (int)(pix / HWg);
+            int rem = (int)(pix - (long long)pn[h] * HWg);
+            const int oy = rem / p.Wg;
+            piy[h] = oy * p.s + p.off;
+            pix_[h] = (rem - oy * p.Wg) * p.s + p.off;
+          }
+        }
+        const uint32_t j8 = (uint32_t)(threadIdx.x & 7);
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int ti = ch / ncg, cg = ch - ti * ncg;
+          const int tap = t0 + ti;
+          const int a = tap / p.k, b = tap - a * p.k;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int q = grp + 16 * h;
+            const int iy = piy[h] + a, ix = pix_[h] + b;
+            const bool good = pok[h] && (unsigned)iy < (unsigned)p.Hx && (unsigned)ix < (unsigned)p.Wx;
+            const float* src = good ? p.x + (((long long)pn[h] * p.Hx + iy) * p.Wx + ix) * p.Cx + c0 + cg * 32 + 4 * j8 : p.x;
+            const uint32_t dst = bbase + (uint32_t)ch * WTC_BLK + (uint32_t)q * 128u +
+                                 ((((j8 >> 1) ^ (uint32_t)(q & 3)) << 5) | ((j8 & 1) << 4));
+            cp_async16_zfill(dst, src, good ? 16u : 0u);
+          }
+        }
+      } else {
+        // thin mode: pixel table in smem (many rows per thread), flattened (tap, channel) slots
+        if (threadIdx.x < 32) {
+          const long long pix = pbeg + (long long)st * WTC_P + threadIdx.x;
+          int ok = pix < pend ? 1 : 0, n = 0, oy = 0, ox = 0;
+          if (ok) {
+            n = (int)(pix / HWg);
+            int rem = (int)(pix - (long long)n * HWg);
+            oy = rem / p.Wg;
+            ox = rem - oy * p.Wg;
+          }
+          asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(ptab + (uint32_t)(s * 32 + threadIdx.x) * 16u), "r"(n),
+                       "r"(oy * p.s + p.off), "r"(ox * p.s + p.off), "r"(ok)
+                       : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int kf = ch * 32 + slot * (p.cs >> 2);
+          const bool kok = kf < p.Kflat;
+          const int tap = kok ? kf / p.Cx : 0;
+          const int cch = kok ? kf - tap * p.Cx : 0;
+          const int a = tap / p.k, b = tap - a * p.k;
+          const uint32_t boff = (uint32_t)(slot * p.cs);
+          for (int q = rr; q < WTC_P; q += rpp) {
+            int n, iy, ix, ok;
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(n), "=r"(iy), "=r"(ix), "=r"(ok) : "r"(ptab + (uint32_t)(s * 32 + q) * 16u));
+            iy += a;
+            ix += b;
+            const bool good = kok && ok && (unsigned)iy < (unsigned)p.Hx && (unsigned)ix < (unsigned)p.Wx;
+            const float* src = good ? p.x + (((long long)n * p.Hx + iy) * p.Wx + ix) * p.Cx + cch : p.x;
+            const uint32_t dst = bbase + (uint32_t)ch * WTC_BLK + (uint32_t)q * 128u +
+                                 (((((boff >> 5) ^ (uint32_t)(q & 3))) << 5) | (boff & 31u));
+            if (p.cs == 16) cp_async16_zfill(dst, src, good ? 16u : 0u);
+            else if (p.cs == 8) cp_async8_zfill(dst, src, good ? 8u : 0u);
+            else cp_async4_zfill(dst, src, good ? 4u : 0u);
+          }
         }
       }
       cp_async_commit();
@@ -548,6 +663,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
     }
     const int r_own = warp * 32 + lane;
     const int rsub = lane >> 3;
+    const uint32_t j = (uint32_t)(lane & 7);
     const uint32_t stg = smem_base;  // stage 0's G region (16 KB), idle now
     float* __restrict__ pbase = p.part + (long long)blockIdx.z * p.Cm * p.K;
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
@@ -569,7 +685,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
                      : "memory");
       __syncwarp();
       const int ti = cc / p.Nc, cin = cc - ti * p.Nc;
-      const long long colofs = (long long)(t0 + ti) * p.Cx + c0 + cin + 4 * j;
+      const long long colofs = p.cs ? (long long)(cc + 4 * j) : (long long)(t0 + ti) * p.Cx + c0 + cin + 4 * j;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = warp * 32 + i * 4 + rsub;
@@ -578,7 +694,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
                      : "r"(stg + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
-        if (m < p.Cm) *reinterpret_cast<float4*>(pbase + (long long)m * p.K + colofs) = o;
+        if (m < p.Cm) {
+          float* dstp = pbase + (long long)m * p.K + colofs;
+          if (colofs + 3 < p.K && (p.K & 3) == 0) {
+            *reinterpret_cast<float4*>(dstp) = o;
+          } else {
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (colofs + e < p.K) dstp[e] = ov[e];
+          }
+        }
       }
       __syncwarp();
     }
@@ -609,7 +735,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
         for (int ti = 0; ti < p.TT; ++ti) {
 #pragma unroll
           for (int kg = 0; kg < 4; ++kg) {
-            const uint32_t lbo = (uint32_t)WTC_BLK, sbo = (p.variant & 1) ? 1024u : 512u;
+            const uint32_t lbo = (uint32_t)WTC_BLK, sbo = 512u;
             umma_tf32(tmem_acc + (uint32_t)(ti * p.Nc), make_sw128b32_mnmajor_desc(a_addr + kg * 1024, lbo, sbo),
                       make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(ti * ncg) * WTC_BLK + kg * 1024, lbo, sbo), idesc,
                       (uint32_t)((st | kg) != 0));
@@ -626,19 +752,33 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
 }
 
 // plan shared by the workspace query and the launch
-struct WTcPlan { int ok, TT, Nc, tmem_cols, splits; long long pps; };
+struct WTcPlan { int ok, TT, Nc, tmem_cols, splits, cs, ctiles; long long pps; };
 static WTcPlan wgrad_tc_plan(const EquivConv& e) {
   WTcPlan w{};
-  if ((e.I % 32) != 0 || (e.O % 32) != 0) return w;
+  if ((e.O % 4) != 0) return w;                 // the G tile is a TMA box: row stride must be a multiple of 16 B
   const int taps = e.k * e.k;
-  int Nc = e.I >= 256 && e.I % 256 == 0 ? 256 : (e.I % 128 == 0 ? 128 : (e.I % 64 == 0 ? 64 : 32));
-  int TT = 256 / Nc;
-  while (TT > 1 && (taps % TT) != 0) TT >>= 1;
+  int Nc, TT;
+  if ((e.I % 32) == 0) {
+    Nc = e.I % 256 == 0 ? 256 : (e.I % 128 == 0 ? 128 : (e.I % 64 == 0 ? 64 : 32));
+    TT = 256 / Nc;
+    while (TT > 1 && (taps % TT) != 0) TT >>= 1;
+    w.cs = 0;
+    w.ctiles = (taps / TT) * (e.I / Nc);
+  } else {
+    // thin X (image side): all k*k*I flattened columns in one CTA column tile
+    const int kflat = taps * e.I;
+    Nc = (kflat + 31) / 32 * 32;
+    if (e.I > 32 || Nc > 256) return w;
+    TT = 1;
+    w.cs = (e.I % 4 == 0) ? 16 : ((e.I % 2 == 0) ? 8 : 4);
+    if (32 % e.I != 0 && w.cs != 4) w.cs = 4;
+    w.ctiles = 1;
+  }
   w.Nc = Nc; w.TT = TT;
   int cols = TT * Nc;
   w.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : 256));
   const long long P = (long long)e.N * e.Hs * e.Ws;
-  const long long tiles = (long long)(taps / TT) * (e.I / Nc) * ceil_div(e.O, 128);
+  const long long tiles = (long long)w.ctiles * ceil_div(e.O, 128);
   long long s = ceil_div64(2LL * 2 * sm_count(), tiles);
   long long maxs = ceil_div64(P, 8 * WTC_P);
   if (s > maxs) s = maxs;
@@ -678,7 +818,7 @@ int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* 
   p.k = e.k; p.s = e.s; p.off = -e.p; p.K = e.k * e.k * e.I;
   p.P = (long long)e.N * e.Hs * e.Ws; p.p_per_split = w.pps;
   p.TT = w.TT; p.Nc = w.Nc; p.tmem_cols = w.tmem_cols;
-  { const char* ev = getenv("SGK_WGRAD_VARIANT"); p.variant = ev ? atoi(ev) : 0; }
+  p.cs = w.cs; p.Kflat = e.k * e.k * e.I;
   cuuint64_t gdim[2] = {(cuuint64_t)e.O, (cuuint64_t)p.P};
   cuuint64_t gstr[1] = {(cuuint64_t)e.O * sizeof(float)};
   cuuint32_t box[2] = {32u, (cuuint32_t)WTC_P};
@@ -688,14 +828,14 @@ int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* 
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(G) failed (%d)", (int)r); return SGK_ECUDA; }
   const uint32_t stage_bytes = WTC_A_BYTES + (uint32_t)w.TT * (w.Nc / 32) * WTC_BLK;
-  const size_t smem = (size_t)WTC_STAGES * stage_bytes + 8 * (2 * WTC_STAGES + 2) + 1024;
+  const size_t smem = (size_t)WTC_STAGES * stage_bytes + 8 * (2 * WTC_STAGES + 2) + WTC_STAGES * 32 * 16 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t ce = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(conv_wgrad_tc_kernel)");
     attr_done = true;
   }
-  dim3 grid((unsigned)((e.k * e.k / w.TT) * (e.I / w.Nc)), (unsigned)ceil_div(e.O, 128), (unsigned)w.splits);
+  dim3 grid((unsigned)w.ctiles, (unsigned)ceil_div(e.O, 128), (unsigned)w.splits);
   conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, map);
   SGK_LAUNCH_CHECK("conv_wgrad_tc_kernel");
   return launch_wgrad_reduce((const float*)ws, dw, e.O, e.I, e.k, w.splits, st);

@@ -1,0 +1,116 @@
+"""GPU parity of the tensor-core path (SGK_TF32: tcgen05.mma kind::tf32, fp32 storage, fp32 accumulation in TMEM).
+Stated tolerances (SURVEY 8c calibration for tf32 operands: outputs 7e-4, loss 2e-5..1e-3, gradients up to 1e-1 with
+cosine >= 0.994):
+  * per conv (fwd / dgrad / wgrad) vs the numpy fp64 oracle: <= 2e-3 of the tensor's max magnitude
+  * config-1 networks at fixed weights vs the fp64 oracle: G output <= 3e-3 abs, loss <= 2e-3 rel,
+    parameter gradients: cosine >= 0.99 and relative L2 <= 0.15
+The fp32 CUDA-core path (all other GPU tests) is the strict-parity mode."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets as ON
+from oracle import ops_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def S():
+    import os
+    os.environ["SGK_TC_THIN"] = "1"   # also exercise the tensor-core tile on thin-channel layers (off by default: slower)
+    import supervised_gan_b200 as S
+    S.set_precision("tf32")
+    yield S
+    S.set_precision("fp32")
+
+
+def dev(a):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda")
+
+
+def nhwc(a):
+    return dev(np.transpose(a, (0, 2, 3, 1)))
+
+
+def nchw(t):
+    return np.transpose(t.detach().cpu().double().numpy(), (0, 3, 1, 2))
+
+
+def rel(got, ref):
+    return np.abs(np.asarray(got, dtype=np.float64) - ref).max() / max(np.abs(ref).max(), 1e-9)
+
+
+TC_CASES = [  # transposed, N, Cin, Cout, H, W, k, s, p  (all channel counts multiples of 32 -> tensor-core kernels)
+    (0, 2, 32, 64, 33, 29, 4, 2, 2), (0, 1, 64, 128, 17, 17, 4, 1, 2), (0, 2, 128, 256, 18, 18, 4, 1, 2),
+    (0, 1, 256, 512, 9, 9, 4, 2, 1), (0, 1, 64, 64, 20, 24, 3, 1, 1), (0, 1, 128, 64, 12, 12, 3, 1, 1),
+    (1, 2, 64, 32, 9, 7, 4, 2, 1), (1, 2, 256, 256, 8, 8, 4, 2, 1), (1, 1, 512, 128, 6, 6, 4, 2, 1),
+    (0, 3, 32, 32, 130, 5, 4, 2, 2),   # > 1 M tile with a ragged tail
+    # thin-channel layers: tap-packed K blocks (Cin < 32) and 16-wide N tiles (Cout <= 16)
+    (0, 2, 2, 32, 33, 40, 4, 2, 2), (1, 2, 32, 2, 16, 16, 4, 2, 1), (0, 2, 128, 1, 18, 18, 4, 1, 2),
+    (0, 2, 3, 64, 20, 20, 4, 2, 2), (1, 2, 8, 256, 8, 8, 4, 2, 1), (0, 1, 10, 64, 8, 8, 3, 1, 1),
+    (0, 1, 2, 64, 16, 16, 3, 1, 1), (0, 1, 64, 1, 16, 16, 3, 1, 1), (1, 1, 128, 1, 8, 8, 4, 2, 1), (0, 1, 1, 32, 32, 32, 4, 2, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tf32(S, case):
+    tr, N, Ci, Co, H, W, k, s, p = case
+    rng = np.random.default_rng(abs(hash(case)) % (2 ** 31))
+    x = rng.standard_normal((N, Ci, H, W))
+    w = rng.standard_normal((Ci, Co, k, k) if tr else (Co, Ci, k, k)) * 0.1
+    b = rng.standard_normal(Co)
+    if tr:
+        y = O.conv_transpose2d_fwd(x, w, b, s, p)
+    else:
+        y = O.conv2d_fwd(x, w, b, s, p)
+    dy = rng.standard_normal(y.shape)
+    if tr:
+        dx = O.conv_transpose2d_dgrad(dy, w, s, p); dw, db = O.conv_transpose2d_wgrad(dy, x, w.shape, s, p)
+    else:
+        dx = O.conv2d_dgrad(dy, w, x.shape, s, p); dw, db = O.conv2d_wgrad(dy, x, w.shape, s, p)
+    cfg = S.ops.ConvCfg(bool(tr), k, s, p)
+    xt, wt, bt = nhwc(x).requires_grad_(True), dev(w).requires_grad_(True), dev(b).requires_grad_(True)
+    n0 = S._lib.load().sgk_launch_count()
+    yt = S.ops.conv(xt, wt, bt, cfg)
+    yt.backward(nhwc(dy))
+    assert rel(nchw(yt), y) <= 2e-3
+    assert rel(nchw(xt.grad), dx) <= 2e-3
+    assert rel(wt.grad.cpu().numpy(), dw) <= 2e-3
+    assert rel(bt.grad.cpu().numpy(), db) <= 1e-4
+    assert S._lib.load().sgk_launch_count() > n0
+
+
+def test_config1_networks_tf32_vs_fp64(S):
+    gen = torch.Generator().manual_seed(5)
+    sdG = ON.init_fcgan_generator(gen, 8, 2, 32, 5)
+    sdDs = [ON.init_nlayer_discriminator(gen, 2, 32, 3, s) for s in (1, 2, 4)]
+    z = torch.randn(2, 8, 4, 4, generator=gen)
+    lam = (0.5, 0.4, 0.1)
+    sg = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.double() if v.is_floating_point() else v.clone())
+          for k, v in sdG.items()}
+    sds = [{k: v.double() for k, v in sd.items()} for sd in sdDs]
+    fake64 = ON.fcgan_generator(sg, z.double(), 5, True)
+    loss64 = sum(l * ON.gan_loss(ON.nlayer_discriminator(sd, fake64, 3, s, True), True) for l, sd, s in zip(lam, sds, (1, 2, 4)))
+    loss64.backward()
+    nw = S.networks
+    G = nw.define_G(2, 0, 32, "fcgan", "instance", False, n_layers_G=5, use_fcn=True, noise_nc=8, gpu_ids=[])
+    G.load_state_dict(sdG); G.cuda()
+    crit = nw.GANLoss(use_lsgan=False)
+    fake = G(z.cuda())
+    loss = 0
+    for l, s, sd in zip(lam, (1, 2, 4), sdDs):
+        D = nw.define_D(2, 32, "n_layers", n_layers_D=3, norm="instance", use_sigmoid=True, scale_factor=s, gpu_ids=[])
+        D.load_state_dict(sd); D.cuda()
+        loss = loss + crit(D(fake), True) * l
+    loss.backward()
+    assert np.abs(fake.detach().cpu().double().numpy() - fake64.detach().numpy()).max() <= 3e-3
+    assert abs(float(loss) - float(loss64)) <= 2e-3 * abs(float(loss64))
+    for k, p in G.named_parameters():
+        ref = sg[k].grad.numpy().ravel()
+        got = p.grad.cpu().double().numpy().ravel()
+        if np.abs(ref).max() < 1e-12:
+            continue  # conv biases feeding a norm: exactly zero on both sides
+        cos = float(got @ ref / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+        l2 = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        assert cos >= 0.99 and l2 <= 0.15, (k, cos, l2)
