@@ -89,12 +89,34 @@ class FCGANModel(object):
         self.batch_D_passes = getattr(opt, "batch_D_passes", True) and opt.norm == 'instance'
         self.skip_unused_grads = getattr(opt, "skip_unused_grads", True)
         self.grad_sync = None  # data-parallel hook: callable(list_of_params, tag) run between backward and step
+        # opt.cuda_graph: after `graph_warmup` eager steps the whole step (G fwd, D phase, Adam, G phase, Adam -- and the
+        # NCCL all-reduces under data parallelism) is captured once and replayed; nothing in the step touches the host.
+        # Requires pool_size == 0 (the image pool draws from Python's `random`) and a fixed batch shape.
+        self.use_graph = bool(getattr(opt, "cuda_graph", False)) and self.isTrain and opt.pool_size == 0
+        self._graph = None
+        self._side = None
+        self._stage = None
+        self._eager_steps = 0
+        self._graph_warmup = int(getattr(opt, "graph_warmup", 3))
 
     # ------------------------------------------------------------------ data
     def set_input(self, input):
         AorB = self.opt.which_direction == 'A'
-        data = input['A' if AorB else 'B'].index_select(1, self.chnl_idx_input)
+        src = input['A' if AorB else 'B']
+        if src.is_cuda or src.is_pinned():
+            # one asynchronous H2D copy of the whole batch, channel selection on the device (the reference selects on the
+            # host into pageable memory, fcgan_model.py:118-122)
+            if self._stage is None or self._stage.shape != src.shape:
+                self._stage = torch.empty(src.shape, device=self.device)
+                self._idx_dev = self.chnl_idx_input.to(self.device)
+            self._stage.copy_(src, non_blocking=True)
+            data = self._stage.index_select(1, self._idx_dev)
+        else:
+            data = src.index_select(1, self.chnl_idx_input)
         if self.input.shape != data.shape:
+            if self._graph is not None:
+                raise RuntimeError("cuda_graph: the batch shape is frozen after capture (got %s, captured %s)"
+                                   % (tuple(data.shape), tuple(self.input.shape)))
             self.input = torch.empty(data.shape, device=self.device)
         self.input.copy_(data, non_blocking=True)
         self.image_paths = input['A_paths' if AorB else 'B_paths']
@@ -163,6 +185,34 @@ class FCGANModel(object):
                     p.requires_grad_(True)
 
     def optimize_parameters(self):
+        if self._graph is not None:
+            self._graph.replay()
+            ops.bump_weights_epoch()
+            return
+        if self.use_graph and self._eager_steps >= self._graph_warmup:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._optimize_parameters_eager()
+            self._graph = graph
+            graph.replay()          # capture does not execute: run the step this call stands for
+            ops.bump_weights_epoch()
+            return
+        self._eager_steps += 1
+        if self.use_graph:
+            # warm-up steps of graph mode run on a side stream: autograd's AccumulateGrad nodes remember the stream they
+            # were created on, and the legacy default stream cannot be joined from a capturing stream
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._optimize_parameters_eager()
+            cur.wait_stream(self._side)
+            return
+        self._optimize_parameters_eager()
+
+    def _optimize_parameters_eager(self):
         self.forward()
         for _ in range(self.opt.n_update_D):
             self.optimizer_D.zero_grad(set_to_none=True)

@@ -179,3 +179,38 @@ def test_fcgan_step_config1_vs_oracle(S):
             assert d.max() <= 2.2 * lr * 2, ("D", i, k, d.max())
             if "model." + k not in zeroD[i]:
                 assert d.mean() <= 0.15 * lr * 2, ("D", i, k, d.mean())
+
+
+def test_cuda_graph_mode_replays_the_whole_step(S):
+    """opt.cuda_graph: 3 eager warm-up steps, capture, then replays.  With the noise fixed (same buffer every step) the
+    graph-replayed step must produce bit-identical losses and weights to the eager step from the same starting point."""
+    from supervised_gan_b200.fcgan_model import FCGANModel
+    gen = torch.Generator().manual_seed(3)
+    sdG = ON.init_fcgan_generator(gen, 8, 2, 8, 5)
+    sdDs = [ON.init_nlayer_discriminator(gen, 2, 8, 3, s) for s in (1, 2, 4)]
+    real = (torch.rand(2, 2, 128, 128, generator=gen) * 2 - 1).cuda()
+    noise = torch.randn(2, 8, 2, 2, generator=gen).cuda()
+
+    def run(use_graph, steps):
+        m = FCGANModel(); m.initialize(make_opt(pool_size=0, batchSize=2, fineSize=128, noiseSize=2, ngf=8, ndf=8, cuda_graph=use_graph))
+        m.netG.load_state_dict(sdG)
+        for d, sd in zip(m.netD, sdDs):
+            d.load_state_dict(sd)
+        S.ops.bump_weights_epoch()
+        m._draw_noise = lambda: noise            # same device buffer in eager and captured steps
+        m.input = real.clone()
+        out = []
+        for _ in range(steps):
+            m.optimize_parameters()
+            out.append([float(m.loss_G), float(m.loss_D_real), float(m.loss_D_fake)])
+        return m, out
+
+    m_e, l_e = run(False, 6)
+    m_g, l_g = run(True, 6)
+    assert m_g._graph is not None and m_e._graph is None
+    assert l_e == l_g
+    for (k, a), (_, b) in zip(m_e.netG.state_dict().items(), m_g.netG.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert m_g.optimizer_G.step_count() == 6
+    with pytest.raises(RuntimeError):
+        m_g.set_input({"A": torch.zeros(3, 3, 128, 128), "A_paths": ["x"]})
