@@ -155,7 +155,7 @@ constexpr int TC_THREADS = 192;
 constexpr int TC_A_BYTES = TC_BM * 128;  // 128 rows x 32 fp32
 
 template <int LAG>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 4)
 conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -190,10 +190,12 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
     const int ok = m < M ? 1 : 0;
     int n = 0, oy = 0, ox = 0;
     if (ok) {
-      n = (int)(m / HWp);
-      int rem = (int)(m - (long long)n * HWp);
-      oy = rem / P.Wp;
-      ox = rem - oy * P.Wp;
+      // 32-bit arithmetic (host guarantees M < 2^31): 64-bit division is a ~100-instruction emulation
+      const unsigned mu = (unsigned)m;
+      n = (int)(mu / (unsigned)HWp);
+      const unsigned rem = mu - (unsigned)n * (unsigned)HWp;
+      oy = (int)(rem / (unsigned)P.Wp);
+      ox = (int)(rem - (unsigned)oy * (unsigned)P.Wp);
     }
     const int iy0 = oy * P.is + P.ioy, ix0 = ox * P.is + P.iox;
     asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(rowinfo + 16u * r), "r"(n), "r"(iy0), "r"(ix0), "r"(ok));
@@ -432,7 +434,11 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   p.tmem_cols = BN < 32 ? 32 : BN;
   p.cs = cs;
   const uint32_t stage_bytes = TC_A_BYTES + BN * 128;
-  int stages = (int)(98304 / stage_bytes);
+  // Few k-blocks per tile make the kernel latency-bound: prefer MORE resident CTAs (2 stages each, up to 4-5 CTAs/SM
+  // for narrow N tiles) over deeper per-CTA pipelines.  SGK_TC_STAGES overrides (experiments).
+  int stages = 2;
+  { const char* ev = getenv("SGK_TC_STAGES"); if (ev) stages = atoi(ev); }
+  if (stages * stage_bytes > 98304) stages = (int)(98304 / stage_bytes);
   if (stages > 4) stages = 4;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -519,7 +525,7 @@ constexpr int WTC_BLK = WTC_P * 128;            // one 32-channel block of a sta
 constexpr int WTC_A_BYTES = 4 * WTC_BLK;        // 128 G channels
 constexpr int WTC_STAGES = 2;
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 3)
 conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant__ WTcMap map) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -760,7 +766,10 @@ static WTcPlan wgrad_tc_plan(const EquivConv& e) {
   int Nc, TT;
   if ((e.I % 32) == 0) {
     Nc = e.I % 256 == 0 ? 256 : (e.I % 128 == 0 ? 128 : (e.I % 64 == 0 ? 64 : 32));
-    TT = 256 / Nc;
+    int cols = 256;
+    { const char* ev = getenv("SGK_WTC_COLS"); if (ev) cols = atoi(ev); }
+    if (Nc > cols) Nc = cols;
+    TT = cols / Nc;
     while (TT > 1 && (taps % TT) != 0) TT >>= 1;
     w.cs = 0;
     w.ctiles = (taps / TT) * (e.I / Nc);
