@@ -326,6 +326,134 @@ static void launch_thin(const FParams& p, long long pixels, int Cg, cudaStream_t
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// thin-output TRANSPOSED gather (ConvT fat->image, Conv dgrad image<-fat): smem-tiled, all sub-pixel phases of a
+// small-grid position computed by one thread.  The phase-by-phase formulation above re-reads the fat tensor from L2
+// once per phase (x4) and per tap (x4); here a CTA stages a (TSH+halo) x (TSW+halo) patch of the fat tensor in shared
+// memory ONCE (coalesced float4 loads, zero-filled borders), keeps every phase's packed weights in shared memory
+// (warp-uniform broadcast reads), and each of the 256 threads produces the s x s output block of its anchor pixel.
+// HBM traffic = fat tensor read once (+halo) + image written once.
+// ------------------------------------------------------------------------------------------------
+constexpr int TT_SH = 8, TT_SW = 32;
+struct ThinTParams {
+  FParams f;
+  int lo_y, lo_x;       // smallest input offset over phases (patch origin relative to the anchor)
+  int halo_y, halo_x;   // extra patch rows / cols beyond the tile
+  int pitch;            // floats per patch pixel (Cg + 4: conflict-free float4 reads across lanes)
+  int Ha, Wa;           // anchor grid = max over phases of (Hp, Wp)
+};
+
+template <int CO>
+__global__ void __launch_bounds__(256) gather_thin_transposed_tile(const __grid_constant__ ThinTParams q) {
+  extern __shared__ __align__(16) float tsm[];
+  const FParams& p = q.f;
+  const int PH = TT_SH + q.halo_y, PW = TT_SW + q.halo_x;
+  float* patch = tsm;                                   // [PH][PW][pitch]
+  float* wsm = tsm + (size_t)PH * PW * q.pitch;         // packed weights of all phases
+  const int n = blockIdx.z;
+  const int ay0 = blockIdx.y * TT_SH, ax0 = blockIdx.x * TT_SW;
+  const int C4 = p.Cg >> 2;
+  // ---- stage the patch (coalesced: consecutive threads -> consecutive float4 of consecutive pixels)
+  const float* __restrict__ in_n = p.in + (long long)n * p.Hi * p.Wi * p.Cg;
+  for (int idx = threadIdx.x; idx < PH * PW * C4; idx += 256) {
+    const int c4 = idx % C4;
+    const int pix = idx / C4;
+    const int px = pix % PW, py = pix / PW;
+    const int iy = ay0 + py + q.lo_y, ix = ax0 + px + q.lo_x;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi)
+      v = __ldg(reinterpret_cast<const float4*>(in_n + ((long long)iy * p.Wi + ix) * p.Cg) + c4);
+    *reinterpret_cast<float4*>(patch + (size_t)pix * q.pitch + 4 * c4) = v;
+  }
+  // ---- stage the weights: phase ph occupies [w_off, w_off + Co*kstride)
+  {
+    const GatherPhase& L = p.ph[p.nphase - 1];
+    const int wtot = (int)L.w_off + p.Co * L.kstride;
+    for (int i = threadIdx.x; i < wtot; i += 256) wsm[i] = __ldg(p.w + i);
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+  const int ay = ay0 + ty, ax = ax0 + tx;
+  float bv[CO];
+#pragma unroll
+  for (int j = 0; j < CO; ++j) bv[j] = (p.bias != nullptr && j < p.Co) ? __ldg(p.bias + j) : 0.f;
+  for (int ph = 0; ph < p.nphase; ++ph) {
+    const GatherPhase& P = p.ph[ph];
+    if (ay >= P.Hp || ax >= P.Wp) continue;
+    float acc[CO];
+#pragma unroll
+    for (int j = 0; j < CO; ++j) acc[j] = 0.f;
+    const float* wp = wsm + P.w_off;
+    for (int a = 0; a < P.ta; ++a) {
+      const int py = ty + a + P.ioy - q.lo_y;
+      for (int b = 0; b < P.tb; ++b) {
+        const int px = tx + b + P.iox - q.lo_x;
+        const float* xp = patch + ((size_t)py * PW + px) * q.pitch;
+        const float* wt = wp + (a * P.tb + b) * p.Cg;
+        for (int c = 0; c < p.Cg; c += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(xp + c);
+#pragma unroll
+          for (int j = 0; j < CO; ++j) {
+            if (j < p.Co) {
+              const float4 w = *reinterpret_cast<const float4*>(wt + j * P.kstride + c);
+              acc[j] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[j]))));
+            }
+          }
+        }
+      }
+    }
+    float* o = p.out + (((long long)n * p.Ho + (ay * P.os + P.ooy)) * p.Wo + (ax * P.os + P.oox)) * p.Co;
+#pragma unroll
+    for (int j = 0; j < CO; ++j)
+      if (j < p.Co) o[j] = act_apply(acc[j] + bv[j], p.act, p.slope);
+  }
+}
+
+// returns true if the tiled kernel was launched
+static bool try_launch_thin_transposed(const GatherPlan& g, const FParams& p, cudaStream_t st, int* rc) {
+  if (!g.transposed_type || g.Co > 4 || (g.Cg & 3) || g.Cg > 64 || g.nphase < 1) return false;
+  ThinTParams q{};
+  q.f = p;
+  int lo_y = 1 << 30, lo_x = 1 << 30, hi_y = -(1 << 30), hi_x = -(1 << 30), Ha = 0, Wa = 0;
+  for (int i = 0; i < g.nphase; ++i) {
+    const GatherPhase& P = g.ph[i];
+    if (P.is != 1 || P.ta <= 0 || P.tb <= 0) return false;
+    lo_y = P.ioy < lo_y ? P.ioy : lo_y;
+    lo_x = P.iox < lo_x ? P.iox : lo_x;
+    hi_y = P.ioy + P.ta - 1 > hi_y ? P.ioy + P.ta - 1 : hi_y;
+    hi_x = P.iox + P.tb - 1 > hi_x ? P.iox + P.tb - 1 : hi_x;
+    Ha = P.Hp > Ha ? P.Hp : Ha;
+    Wa = P.Wp > Wa ? P.Wp : Wa;
+  }
+  q.lo_y = lo_y; q.lo_x = lo_x; q.halo_y = hi_y - lo_y; q.halo_x = hi_x - lo_x;
+  if (q.halo_y > 4 || q.halo_x > 4) return false;
+  q.pitch = g.Cg + 4;
+  q.Ha = Ha; q.Wa = Wa;
+  const GatherPhase& L = g.ph[g.nphase - 1];
+  const size_t wfl = (size_t)L.w_off + (size_t)g.Co * L.kstride;
+  const size_t smem = ((size_t)(TT_SH + q.halo_y) * (TT_SW + q.halo_x) * q.pitch + wfl) * sizeof(float);
+  if (smem > 100 * 1024) return false;
+  dim3 grid((unsigned)ceil_div(Wa, TT_SW), (unsigned)ceil_div(Ha, TT_SH), (unsigned)g.N);
+  static bool attr[3] = {false, false, false};
+  cudaError_t e = cudaSuccess;
+  if (g.Co <= 1) {
+    if (!attr[0]) { e = cudaFuncSetAttribute(gather_thin_transposed_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr[0] = true; }
+    if (e == cudaSuccess) gather_thin_transposed_tile<1><<<grid, 256, smem, st>>>(q);
+  } else if (g.Co == 2) {
+    if (!attr[1]) { e = cudaFuncSetAttribute(gather_thin_transposed_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr[1] = true; }
+    if (e == cudaSuccess) gather_thin_transposed_tile<2><<<grid, 256, smem, st>>>(q);
+  } else {
+    if (!attr[2]) { e = cudaFuncSetAttribute(gather_thin_transposed_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr[2] = true; }
+    if (e == cudaSuccess) gather_thin_transposed_tile<4><<<grid, 256, smem, st>>>(q);
+  }
+  if (e != cudaSuccess) { *rc = cuda_fail(e, "cudaFuncSetAttribute(gather_thin_transposed_tile)"); return true; }
+  e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { *rc = cuda_fail(e, "gather_thin_transposed_tile"); return true; }
+  count_launch();
+  *rc = SGK_OK;
+  return true;
+}
+
 static int launch_gather(const GatherPlan& g, const float* in, const float* w, const float* bias, float* out, int act,
                          float slope, cudaStream_t st) {
   FParams p{};
@@ -342,6 +470,8 @@ static int launch_gather(const GatherPlan& g, const float* in, const float* w, c
   }
   if (pixels == 0) return SGK_OK;
   if (g.Co <= 4) {
+    int trc = SGK_OK;
+    if (try_launch_thin_transposed(g, p, st, &trc)) return trc;
     if (pixels * 32 / 256 > 0x7fffffffLL) { set_error("conv: grid too large"); return SGK_EUNSUPPORTED; }
     if (g.Co <= 1) launch_thin<1>(p, pixels, g.Cg, st);
     else if (g.Co == 2) launch_thin<2>(p, pixels, g.Cg, st);

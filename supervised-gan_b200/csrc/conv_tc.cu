@@ -375,6 +375,293 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
   if (warp == 4) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
 }
 
+// ================================================================================================
+// Persistent variant of the gather GEMM (default).  One CTA per SM slot loops over (M tile, N tile) pairs with a
+// DOUBLE-BUFFERED accumulator in tensor memory, so the per-tile fixed costs (barrier set-up, TMEM allocation, first-load
+// latency, epilogue) overlap with the main loop of the neighbouring tiles instead of being paid 28 waves in a row:
+//   warps 0-3  A producers (cp.async gather, same image as above); they run ahead across tile boundaries, bounded only by
+//              the smem ring; per tile they first publish the row table (gather origin + output offset of 128 rows)
+//   warp 4     TMEM alloc (2 x BN columns) + TMA weight loads          warp 5   MMA issuer
+//   warps 6-9  epilogue: wait tmem_full[acc] -> tcgen05.ld -> bias/act -> smem transpose (own 16 KB) -> coalesced NHWC
+//              stores -> arrive tmem_empty[acc]; overlaps with the MMAs of the next tile (other accumulator)
+// ================================================================================================
+constexpr int TCP_THREADS = 320;
+
+struct TcpParams {
+  TcParams b;
+  int n_tiles_n;       // N tiles
+  long long total;     // M tiles (all phases) * N tiles
+};
+
+template <int LAG>
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+conv_gather_tc_persist_kernel(const __grid_constant__ TcpParams pp, const __grid_constant__ TcMaps maps) {
+  const TcParams& p = pp.b;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.BN * 128u;
+  const uint32_t stg_base = smem_base + (uint32_t)S * stage_bytes;          // epilogue transpose area: 128 rows x 128 B
+  const uint32_t bar_base = stg_base + TC_A_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 4);
+  const uint32_t tab_base = tmem_slot + 16u;                                 // [2][128] int4 + [2][128] int64
+  auto rowinfo = [&](int a) { return tab_base + (uint32_t)a * 2048u; };
+  auto rowout = [&](int a) { return tab_base + 4096u + (uint32_t)a * 1024u; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 128 + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_acc;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+
+  // tile decode shared by all roles
+  auto tile_info = [&](long long t, int& phi, long long& m0, int& n0) {
+    const long long mt = t / pp.n_tiles_n;
+    n0 = (int)(t - mt * pp.n_tiles_n) * p.BN;
+    phi = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+      if (i < p.nphase && mt >= p.ph[i].m_tile_begin) phi = i;
+    m0 = (mt - p.ph[phi].m_tile_begin) * TC_BM;
+  };
+
+  if (warp < 4) {
+    // =============================================================== A producers
+    const uint32_t j = (uint32_t)(lane & 7);
+    const int rsub = lane >> 3;
+    const int spr = p.cs ? 128 / p.cs : 8;
+    const int rpi = 32 / spr;
+    const int slot = lane % spr, tsub = lane / spr;
+    int g = 0;       // k-blocks issued so far (ring position)
+    int it = 0;      // tiles processed by this CTA
+    for (long long t = blockIdx.x; t < pp.total; t += gridDim.x, ++it) {
+      int phi, n0;
+      long long m0;
+      tile_info(t, phi, m0, n0);
+      const GatherPhase P = p.ph[phi];
+      const int HWp = P.Hp * P.Wp;
+      const long long M = (long long)p.N * HWp;
+      const int Kreal = P.ta * P.tb * p.Cg;
+      const int KB = P.kstride >> 5;
+      const int acc = it & 1;
+      // the table slot of this accumulator is free once the epilogue of tile it-2 has drained it
+      mbar_wait(tempty_bar(acc), (uint32_t)(((it >> 1) & 1) ^ 1));
+      {
+        const int r = threadIdx.x;
+        const long long m = m0 + r;
+        const int ok = m < M ? 1 : 0;
+        int n = 0, oy = 0, ox = 0;
+        if (ok) {
+          const unsigned mu = (unsigned)m;
+          n = (int)(mu / (unsigned)HWp);
+          const unsigned rem = mu - (unsigned)n * (unsigned)HWp;
+          oy = (int)(rem / (unsigned)P.Wp);
+          ox = (int)(rem - (unsigned)oy * (unsigned)P.Wp);
+        }
+        asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(rowinfo(acc) + 16u * r), "r"(n), "r"(oy * P.is + P.ioy),
+                     "r"(ox * P.is + P.iox), "r"(ok)
+                     : "memory");
+        const long long oofs = (((long long)n * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co;
+        asm volatile("st.shared.s64 [%0], %1;" ::"r"(rowout(acc) + 8u * r), "l"(oofs) : "memory");
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // table visible to all producer threads
+      int a = 0, b = 0, c0 = 0;
+      for (int kb = 0; kb < KB; ++kb, ++g) {
+        const int s = g % S;
+        mbar_wait(empty_bar(s), (uint32_t)(((g / S) & 1) ^ 1));
+        const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
+        if (p.cs == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = warp * 32 + i * 4 + rsub;
+            int n, iy, ix, ok;
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(n), "=r"(iy), "=r"(ix), "=r"(ok) : "r"(rowinfo(acc) + 16u * r));
+            iy += a;
+            ix += b;
+            const bool good = ok && (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
+            const float* src = good ? p.in + (((long long)n * p.Hi + iy) * p.Wi + ix) * p.Cg + c0 + 4 * j : p.in;
+            cp_async16_zfill(abase + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4), src, good ? 16u : 0u);
+          }
+        } else {
+          const int k = kb * 32 + slot * (p.cs >> 2);
+          const bool kok = k < Kreal;
+          const int tap = kok ? k / p.Cg : 0;
+          const int cch = kok ? k - tap * p.Cg : 0;
+          const int ta_ = tap / P.tb, tb_ = tap - ta_ * P.tb;
+          const uint32_t boff = (uint32_t)(slot * p.cs);
+          for (int i = 0; i < 32 / rpi; ++i) {
+            const int r = warp * 32 + i * rpi + tsub;
+            int n, iy, ix, ok;
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(n), "=r"(iy), "=r"(ix), "=r"(ok) : "r"(rowinfo(acc) + 16u * r));
+            iy += ta_;
+            ix += tb_;
+            const bool good = kok && ok && (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi;
+            const float* src = good ? p.in + (((long long)n * p.Hi + iy) * p.Wi + ix) * p.Cg + cch : p.in;
+            const uint32_t dst = abase + (uint32_t)r * 128u + ((((boff >> 4) ^ (uint32_t)(r & 7)) << 4) | (boff & 15u));
+            if (p.cs == 16) cp_async16_zfill(dst, src, good ? 16u : 0u);
+            else if (p.cs == 8) cp_async8_zfill(dst, src, good ? 8u : 0u);
+            else cp_async4_zfill(dst, src, good ? 4u : 0u);
+          }
+        }
+        cp_async_commit();
+        if (g >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async();
+          mbar_arrive(full_bar((g - LAG) % S));
+        }
+        c0 += 32;
+        if (c0 >= p.Cg) {
+          c0 = 0;
+          if (++b == P.tb) { b = 0; ++a; }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int q = (g > LAG ? g - LAG : 0); q < g; ++q) mbar_arrive(full_bar(q % S));
+  } else if (warp == 4) {
+    // =============================================================== weight TMA producer
+    if (lane == 0) {
+      const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+      int g = 0;
+      for (long long t = blockIdx.x; t < pp.total; t += gridDim.x) {
+        int phi, n0;
+        long long m0;
+        tile_info(t, phi, m0, n0);
+        const int KB = p.ph[phi].kstride >> 5;
+        const void* tmap = &maps.w[phi];
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int s = g % S;
+          mbar_wait(empty_bar(s), (uint32_t)(((g / S) & 1) ^ 1));
+          mbar_arrive_expect_tx(full_bar(s), b_bytes);
+          tma_load_2d(smem_base + (uint32_t)s * stage_bytes + TC_A_BYTES, tmap, kb * 32, n0, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN);
+      int g = 0, it = 0;
+      for (long long t = blockIdx.x; t < pp.total; t += gridDim.x, ++it) {
+        int phi, n0;
+        long long m0;
+        tile_info(t, phi, m0, n0);
+        const int KB = p.ph[phi].kstride >> 5;
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_acc + (uint32_t)(acc * p.BN);
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int s = g % S;
+          mbar_wait(full_bar(s), (uint32_t)((g / S) & 1));
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+          const uint32_t b_addr = a_addr + TC_A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_tf32(d_tmem, make_sw128_kmajor_desc(a_addr + kk * 32), make_sw128_kmajor_desc(b_addr + kk * 32), idesc,
+                      (uint32_t)((kb | kk) != 0));
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // =============================================================== epilogue warps 6..9 (TMEM lane quarter = warp % 4)
+    const int q4 = warp & 3;
+    const uint32_t j = (uint32_t)(lane & 7);
+    const int rsub = lane >> 3;
+    const int r_own = q4 * 32 + lane;
+    int it = 0;
+    for (long long t = blockIdx.x; t < pp.total; t += gridDim.x, ++it) {
+      int phi, n0;
+      long long m0;
+      tile_info(t, phi, m0, n0);
+      const int acc = it & 1;
+      mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int cc = 0; cc < p.BN; cc += 32) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + (uint32_t)cc, v);
+        tmem_ld_wait();
+        const int ncol = min(32, p.Co - n0 - cc);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float bvv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.bias != nullptr) {
+            if (4 * q + 3 < ncol) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cc + 4 * q));
+              bvv[0] = bv.x; bvv[1] = bv.y; bvv[2] = bv.z; bvv[3] = bv.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (4 * q + e < ncol) bvv[e] = __ldg(p.bias + n0 + cc + 4 * q + e);
+            }
+          }
+          const float o0 = act_apply(__uint_as_float(v[4 * q + 0]) + bvv[0], p.act, p.slope);
+          const float o1 = act_apply(__uint_as_float(v[4 * q + 1]) + bvv[1], p.act, p.slope);
+          const float o2 = act_apply(__uint_as_float(v[4 * q + 2]) + bvv[2], p.act, p.slope);
+          const float o3 = act_apply(__uint_as_float(v[4 * q + 3]) + bvv[3], p.act, p.slope);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + (uint32_t)r_own * 128u +
+                                                                      (((uint32_t)q ^ (uint32_t)(r_own & 7)) << 4)),
+                       "f"(o0), "f"(o1), "f"(o2), "f"(o3)
+                       : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = q4 * 32 + i * 4 + rsub;
+          long long oofs;
+          int ok;
+          asm volatile("ld.shared.s64 %0, [%1];" : "=l"(oofs) : "r"(rowout(acc) + 8u * r));
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ok) : "r"(rowinfo(acc) + 16u * r + 12u));
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "r"(stg_base + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
+          if (ok) {
+            float* dstp = p.out + oofs + n0 + cc + 4 * j;
+            if ((int)(4 * j) + 3 < ncol && (p.Co & 3) == 0) {
+              *reinterpret_cast<float4*>(dstp) = o;
+            } else {
+              const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if ((int)(4 * j) + e < ncol) dstp[e] = ov[e];
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // accumulator (and the row table slot) may be reused
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -459,9 +746,52 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   }
   if (tiles == 0) return SGK_OK;
   if (tiles > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return SGK_EUNSUPPORTED; }
+  // The persistent variant overlaps per-tile fixed costs, but these gathers are bound by loads in flight per SM and the
+  // non-persistent launch with up to 4 resident CTAs keeps more of them in flight (measured: 9.2 vs 9.45 ms of conv per
+  // step); it stays available for experiments with SGK_TC_PERSIST=1.
+  static const bool persist = getenv("SGK_TC_PERSIST") != nullptr && atoi(getenv("SGK_TC_PERSIST")) != 0;
+  const int n_tiles_n = ceil_div(g.Co, BN);
+  if (persist) {
+    // persistent launch: ring of S stages + one 16 KB transpose area + 2 row tables; CTAs per SM from the smem budget
+    int pst = 4;
+    { const char* ev = getenv("SGK_TCP_STAGES"); if (ev) pst = atoi(ev); }
+    const int tm_cols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    int ctas_per_sm = 512 / tm_cols;                     // TMEM budget
+    if (ctas_per_sm > 2) ctas_per_sm = 2;
+    const size_t budget = (size_t)(ctas_per_sm == 2 ? 110 : 220) * 1024;
+    const size_t fixed = TC_A_BYTES + 8 * (2 * 4 + 5) + 16 + 2 * 2048 + 2 * 1024 + 1024;
+    while (pst > 2 && (size_t)pst * stage_bytes + fixed > budget) --pst;
+    TcpParams pp{};
+    pp.b = p;
+    pp.b.stages = pst;
+    pp.b.tmem_cols = tm_cols;
+    pp.n_tiles_n = n_tiles_n;
+    pp.total = tiles * n_tiles_n;
+    const size_t psmem = (size_t)pst * stage_bytes + fixed;
+    long long gridx = (long long)ctas_per_sm * sm_count();
+    if (gridx > pp.total) gridx = pp.total;
+    static bool pattr[2] = {false, false};
+    if (pst == 2) {
+      if (!pattr[0]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gather_tc_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_gather_tc_persist_kernel<1>)");
+        pattr[0] = true;
+      }
+      conv_gather_tc_persist_kernel<1><<<(unsigned)gridx, TCP_THREADS, psmem, st>>>(pp, maps);
+    } else {
+      if (!pattr[1]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gather_tc_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_gather_tc_persist_kernel<2>)");
+        pattr[1] = true;
+      }
+      conv_gather_tc_persist_kernel<2><<<(unsigned)gridx, TCP_THREADS, psmem, st>>>(pp, maps);
+    }
+    SGK_LAUNCH_CHECK("conv_gather_tc_persist_kernel");
+    return SGK_OK;
+  }
   const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 2) + 128 * 24 + 1024;
   static bool attr_done[2] = {false, false};
-  dim3 grid((unsigned)tiles, (unsigned)ceil_div(g.Co, BN));
+  dim3 grid((unsigned)tiles, (unsigned)n_tiles_n);
   if (stages == 2) {
     if (!attr_done[0]) {
       cudaError_t e = cudaFuncSetAttribute(conv_gather_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
