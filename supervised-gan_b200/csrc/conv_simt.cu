@@ -454,6 +454,102 @@ static bool try_launch_thin_transposed(const GatherPlan& g, const FParams& p, cu
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// "image-edge" direct convs: thin gathered side (K = k*k*Cg <= 64: the 1-3 channel image), fat output side (32 channels
+// per warp).  LANES = OUTPUT CHANNELS: every lane keeps the K weights of its channel in registers, the CTA stages the
+// image patch of an 8 x 32 output tile in shared memory, each warp walks one output row and for every pixel reads the
+// K patch values as warp-uniform broadcasts -> K FMAs per lane -> one coalesced 128-B store per pixel.
+// Used by the first PatchGAN / U-Net conv (fwd) and the generators' last ConvT (dgrad).
+// ------------------------------------------------------------------------------------------------
+constexpr int EG_TH = 8, EG_TW = 32;
+template <int TA, int TBC>   // taps rows, contiguous floats per tap row (tb * Cg): compile-time so that k -> patch offset folds
+__global__ void __launch_bounds__(256) edge_direct_kernel(const __grid_constant__ FParams p) {
+  constexpr int KMAX = TA * TBC;
+  extern __shared__ __align__(16) float esm[];
+  const GatherPhase& P = p.ph[0];
+  const int K = KMAX;
+  const int PH = (EG_TH - 1) * P.is + P.ta, PWp = (EG_TW - 1) * P.is + P.tb;   // patch pixels
+  const int rowf = PWp * p.Cg;                                                   // floats per patch row
+  const int cgroups = (p.Co + 31) >> 5;
+  const int n = blockIdx.z / cgroups, cg = blockIdx.z - n * cgroups;
+  const int oy0 = blockIdx.y * EG_TH, ox0 = blockIdx.x * EG_TW;
+  const int iy0 = oy0 * P.is + P.ioy, ix0 = ox0 * P.is + P.iox;
+  const float* __restrict__ in_n = p.in + (long long)n * p.Hi * p.Wi * p.Cg;
+  for (int idx = threadIdx.x; idx < PH * rowf; idx += 256) {
+    const int py = idx / rowf, rem = idx - py * rowf;
+    const int px = rem / p.Cg, c = rem - px * p.Cg;
+    const int iy = iy0 + py, ix = ix0 + px;
+    float v = 0.f;
+    if ((unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi) v = __ldg(in_n + ((long long)iy * p.Wi + ix) * p.Cg + c);
+    esm[idx] = v;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int co = cg * 32 + lane;
+  float w[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) w[k] = (k < K && co < p.Co) ? __ldg(p.w + (long long)co * P.kstride + k) : 0.f;
+  const float bv = (p.bias != nullptr && co < p.Co) ? __ldg(p.bias + co) : 0.f;
+  __syncthreads();
+  const int oy = oy0 + warp;
+  if (oy >= P.Hp) return;
+  const bool vec_ok = ((rowf & 3) == 0) && (((P.is * p.Cg) & 3) == 0);
+  float* __restrict__ orow = p.out + (((long long)n * p.Ho + oy) * p.Wo) * p.Co + co;
+  for (int xl = 0; xl < EG_TW; ++xl) {
+    const int ox = ox0 + xl;
+    if (ox >= P.Wp) break;
+    float acc;
+    const float* pp0 = esm + (warp * P.is) * rowf + xl * P.is * p.Cg;
+    // warp-uniform broadcast reads of the K patch values; 128-bit when the tap rows are 16-B aligned (shared-memory
+    // bandwidth, one wavefront per instruction, is what bounds this kernel); 4 independent FMA chains
+    float a4[4] = {bv, 0.f, 0.f, 0.f};
+    if (TBC % 4 == 0 && vec_ok) {
+#pragma unroll
+      for (int a = 0; a < TA; ++a)
+#pragma unroll
+        for (int r = 0; r < TBC; r += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(pp0 + a * rowf + r);
+          a4[0] = fmaf(v.x, w[a * TBC + r + 0], a4[0]);
+          a4[1] = fmaf(v.y, w[a * TBC + r + 1], a4[1]);
+          a4[2] = fmaf(v.z, w[a * TBC + r + 2], a4[2]);
+          a4[3] = fmaf(v.w, w[a * TBC + r + 3], a4[3]);
+        }
+    } else {
+#pragma unroll
+      for (int a = 0; a < TA; ++a)
+#pragma unroll
+        for (int r = 0; r < TBC; ++r) a4[r & 3] = fmaf(pp0[a * rowf + r], w[a * TBC + r], a4[r & 3]);
+    }
+    acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    if (co < p.Co) orow[(long long)ox * p.Co] = act_apply(acc, p.act, p.slope);
+  }
+}
+
+static bool try_launch_edge_direct(const GatherPlan& g, const FParams& p, cudaStream_t st, int* rc) {
+  if (g.transposed_type || g.nphase != 1) return false;
+  const GatherPhase& P = g.ph[0];
+  if (g.Cg > 4 || g.Co < 32 || P.os != 1 || P.ta != P.tb) return false;
+  const int key = P.ta * 100 + P.tb * g.Cg;
+  if (key != 404 && key != 408 && key != 412 && key != 306 && key != 303 && key != 309) return false;
+  const int PH = (EG_TH - 1) * P.is + P.ta, PWp = (EG_TW - 1) * P.is + P.tb;
+  const size_t smem = (size_t)PH * PWp * g.Cg * sizeof(float);
+  if (smem > 48 * 1024) return false;
+  const int cgroups = (g.Co + 31) / 32;
+  dim3 grid((unsigned)ceil_div(P.Wp, EG_TW), (unsigned)ceil_div(P.Hp, EG_TH), (unsigned)(g.N * cgroups));
+  switch (key) {
+    case 404: edge_direct_kernel<4, 4><<<grid, 256, smem, st>>>(p); break;
+    case 408: edge_direct_kernel<4, 8><<<grid, 256, smem, st>>>(p); break;
+    case 412: edge_direct_kernel<4, 12><<<grid, 256, smem, st>>>(p); break;
+    case 303: edge_direct_kernel<3, 3><<<grid, 256, smem, st>>>(p); break;
+    case 306: edge_direct_kernel<3, 6><<<grid, 256, smem, st>>>(p); break;
+    default: edge_direct_kernel<3, 9><<<grid, 256, smem, st>>>(p); break;
+  }
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { *rc = cuda_fail(e, "edge_direct_kernel"); return true; }
+  count_launch();
+  *rc = SGK_OK;
+  return true;
+}
+
 static int launch_gather(const GatherPlan& g, const float* in, const float* w, const float* bias, float* out, int act,
                          float slope, cudaStream_t st) {
   FParams p{};
@@ -480,6 +576,10 @@ static int launch_gather(const GatherPlan& g, const float* in, const float* w, c
     return SGK_OK;
   }
   if (tiles > 0x7fffffffLL) { set_error("conv: grid too large"); return SGK_EUNSUPPORTED; }
+  {
+    int erc = SGK_OK;
+    if (try_launch_edge_direct(g, p, st, &erc)) return erc;
+  }
   bool vec = (g.Cg % 4) == 0;
   if (g.Co > 32) {
     dim3 grid((unsigned)tiles, (unsigned)ceil_div(g.Co, 64));
@@ -677,6 +777,93 @@ __global__ void __launch_bounds__(256) pixel_reduce_w_thin(const __grid_constant
     *reinterpret_cast<float4*>(part + (long long)m * p.K + j) = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// image-edge weight gradient: dW[m][(a,b,c)] with a thin gathered side (K <= 64) and a fat G side.  LANES = G CHANNELS:
+// each lane accumulates the K gradients of its channel in registers while its warp walks output rows (g value: one
+// coalesced 128-B load per pixel; patch values: warp-uniform smem broadcasts).  Persistent CTAs (grid-stride over
+// tiles), one fixed-order cross-warp reduction and one partial per CTA.
+// ------------------------------------------------------------------------------------------------
+template <int TA, int TBC>
+__global__ void __launch_bounds__(256) edge_wgrad_kernel(const __grid_constant__ WParams p, int tiles_x, int tiles_y) {
+  constexpr int KMAX = TA * TBC;
+  extern __shared__ __align__(16) float wsm[];
+  const int K = KMAX;
+  const int PH = (EG_TH - 1) * p.s + p.k, PWp = (EG_TW - 1) * p.s + p.k;
+  const int rowf = PWp * p.Cx;
+  float* patch = wsm;
+  float* red = wsm + (size_t)PH * rowf;   // [8 warps][32 lanes][KMAX] cross-warp reduction buffer
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cgroups = (p.Cm + 31) >> 5;
+  const long long ntiles = (long long)tiles_x * tiles_y * p.N;
+  const int cg = blockIdx.y;
+  const int m = cg * 32 + lane;
+  float acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  const bool vec_ok = ((rowf & 3) == 0) && (((p.s * p.Cx) & 3) == 0);
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int n = (int)(t / ((long long)tiles_x * tiles_y));
+    const int r2 = (int)(t - (long long)n * tiles_x * tiles_y);
+    const int tyi = r2 / tiles_x, txi = r2 - tyi * tiles_x;
+    const int oy0 = tyi * EG_TH, ox0 = txi * EG_TW;
+    const int iy0 = oy0 * p.s + p.off, ix0 = ox0 * p.s + p.off;
+    const float* __restrict__ xn = p.x + (long long)n * p.Hx * p.Wx * p.Cx;
+    __syncthreads();   // previous tile's patch fully consumed
+    for (int idx = threadIdx.x; idx < PH * rowf; idx += 256) {
+      const int py = idx / rowf, rem = idx - py * rowf;
+      const int px = rem / p.Cx, c = rem - px * p.Cx;
+      const int iy = iy0 + py, ix = ix0 + px;
+      float v = 0.f;
+      if ((unsigned)iy < (unsigned)p.Hx && (unsigned)ix < (unsigned)p.Wx) v = __ldg(xn + ((long long)iy * p.Wx + ix) * p.Cx + c);
+      patch[idx] = v;
+    }
+    __syncthreads();
+    const int oy = oy0 + warp;
+    if (oy < p.Hg) {
+      const float* __restrict__ grow = p.g + (((long long)n * p.Hg + oy) * p.Wg) * p.Cm + m;
+      // all 32 g values of this row segment first (32 independent coalesced loads in flight), then the FMAs
+      float gq[EG_TW];
+#pragma unroll
+      for (int xl = 0; xl < EG_TW; ++xl) gq[xl] = (m < p.Cm && ox0 + xl < p.Wg) ? __ldg(grow + (long long)(ox0 + xl) * p.Cm) : 0.f;
+#pragma unroll 4
+      for (int xl = 0; xl < EG_TW; ++xl) {
+        const float gv = gq[xl];
+        const float* pp0 = patch + (warp * p.s) * rowf + xl * p.s * p.Cx;
+        if (TBC % 4 == 0 && vec_ok) {
+#pragma unroll
+          for (int a = 0; a < TA; ++a)
+#pragma unroll
+            for (int r = 0; r < TBC; r += 4) {
+              const float4 v = *reinterpret_cast<const float4*>(pp0 + a * rowf + r);
+              acc[a * TBC + r + 0] = fmaf(gv, v.x, acc[a * TBC + r + 0]);
+              acc[a * TBC + r + 1] = fmaf(gv, v.y, acc[a * TBC + r + 1]);
+              acc[a * TBC + r + 2] = fmaf(gv, v.z, acc[a * TBC + r + 2]);
+              acc[a * TBC + r + 3] = fmaf(gv, v.w, acc[a * TBC + r + 3]);
+            }
+        } else {
+#pragma unroll
+          for (int a = 0; a < TA; ++a)
+#pragma unroll
+            for (int r = 0; r < TBC; ++r) acc[a * TBC + r] = fmaf(gv, pp0[a * rowf + r], acc[a * TBC + r]);
+        }
+      }
+    }
+  }
+  // fixed-order reduction over the 8 warps, then one partial row block per CTA: part[blockIdx.x][m][k]
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) red[((size_t)warp * 32 + lane) * KMAX + k] = acc[k];
+  __syncthreads();
+  if (warp == 0 && m < p.Cm) {
+    float* dst = p.part + ((long long)blockIdx.x * p.Cm + m) * K;
+    for (int k = 0; k < K; ++k) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) sacc += red[((size_t)wq * 32 + lane) * KMAX + k];
+      dst[k] = sacc;
+    }
+  }
+}
+
 // ordered reduction over splits and scatter into the reference layout raw[O][I][k][k].
 // A group of RL lanes owns 4 consecutive packed outputs (one float4 per split): lanes stride over the splits with
 // independent loads in flight, then a fixed-order shuffle reduction -- deterministic, and bandwidth- rather than
@@ -827,8 +1014,10 @@ extern "C" size_t sgk_conv_wgrad_workspace_bytes(const SgkConvDesc* d) {
   size_t a = (size_t)splits * e.O * e.I * e.k * e.k * sizeof(float);
   size_t b = sgk_bias_grad_workspace_bytes((size_t)d->N * d->Hout * d->Wout, d->Cout);
   size_t c = d->precision != SGK_FP32 ? conv_wgrad_tc_workspace_bytes(d) : 0;
+  size_t dd = (size_t)2 * sm_count() * e.O * e.I * e.k * e.k * sizeof(float);   // image-edge kernel: one partial per CTA
   a = a > b ? a : b;
-  return a > c ? a : c;
+  a = a > c ? a : c;
+  return a > dd ? a : dd;
 }
 
 extern "C" int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float* dy, float* dw, float* dbias,
@@ -845,6 +1034,49 @@ extern "C" int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float*
     if (need > workspace_bytes) { set_error("sgk_conv_wgrad: workspace too small for bias grad"); return SGK_EWORKSPACE; }
     rc = sgk_bias_grad(dy, dbias, rows, d->Cout, workspace, workspace_bytes, stream);
     if (rc) return rc;
+  }
+  // image-edge layers (thin gathered side, K <= 64; fat G side): lanes-as-channels CUDA-core kernel, exact fp32
+  const int ekey = e.k * 100 + e.k * e.I;
+  if (e.I <= 4 && e.O >= 32 && (ekey == 404 || ekey == 408 || ekey == 412 || ekey == 303 || ekey == 306 || ekey == 309)) {
+    const int K = e.k * e.k * e.I;
+    const int tiles_x = ceil_div(e.Ws, EG_TW), tiles_y = ceil_div(e.Hs, EG_TH);
+    long long ntiles = (long long)tiles_x * tiles_y * e.N;
+    const int cgroups = ceil_div(e.O, 32);
+    long long ctas = 2LL * sm_count() / cgroups;
+    if (ctas < 1) ctas = 1;
+    if (ctas > ntiles) ctas = ntiles;
+    const size_t need_e = (size_t)ctas * e.O * K * sizeof(float);
+    const int KMAX = K;
+    const int PH = (EG_TH - 1) * e.s + e.k, PWp = (EG_TW - 1) * e.s + e.k;
+    const size_t smem = ((size_t)PH * PWp * e.I + (size_t)8 * 32 * KMAX) * sizeof(float);
+    if (need_e <= workspace_bytes && smem <= 100 * 1024) {
+      WParams q{};
+      q.g = d->transposed ? x : dy;
+      q.x = d->transposed ? dy : x;
+      q.part = (float*)workspace;
+      q.N = e.N; q.Hg = e.Hs; q.Wg = e.Ws; q.Cm = e.O; q.Hx = e.Hb; q.Wx = e.Wb; q.Cx = e.I;
+      q.k = e.k; q.s = e.s; q.off = -e.p; q.K = K; q.P = (long long)e.N * e.Hs * e.Ws; q.p_per_split = 0;
+      dim3 grid((unsigned)ctas, (unsigned)cgroups);
+      cudaError_t ce = cudaSuccess;
+#define SGK_EDGE_W(TA_, TBC_)                                                                                           \
+  {                                                                                                                     \
+    static bool done = false;                                                                                           \
+    if (!done) { ce = cudaFuncSetAttribute(edge_wgrad_kernel<TA_, TBC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done = true; } \
+    if (ce == cudaSuccess) edge_wgrad_kernel<TA_, TBC_><<<grid, 256, smem, st>>>(q, tiles_x, tiles_y);                   \
+  }
+      switch (ekey) {
+        case 404: SGK_EDGE_W(4, 4) break;
+        case 408: SGK_EDGE_W(4, 8) break;
+        case 412: SGK_EDGE_W(4, 12) break;
+        case 303: SGK_EDGE_W(3, 3) break;
+        case 306: SGK_EDGE_W(3, 6) break;
+        default: SGK_EDGE_W(3, 9) break;
+      }
+#undef SGK_EDGE_W
+      if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(edge_wgrad_kernel)");
+      SGK_LAUNCH_CHECK("edge_wgrad_kernel");
+      return launch_wgrad_reduce((const float*)workspace, dw, e.O, e.I, e.k, (int)ctas, st);
+    }
   }
   if (d->precision != SGK_FP32) {
     rc = conv_wgrad_tc(d, x, dy, dw, workspace, workspace_bytes, st);
