@@ -903,20 +903,27 @@ __global__ void __launch_bounds__(256) wgrad_reduce_vec_kernel(const float* __re
   }
 }
 
-__global__ void wgrad_reduce_scalar_kernel(const float* __restrict__ part, float* __restrict__ dw, int O, int I, int k,
-                                           int splits) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)O * I * k * k;
-  if (idx >= total) return;
-  int i = (int)(idx % I);
-  long long tt = idx / I;
-  int b = (int)(tt % k);
-  tt /= k;
-  int a = (int)(tt % k);
-  int o = (int)(tt / k);
+// any I (thin layers): RL lanes per output element stride over the splits, fixed-order shuffle reduction
+template <int RL>
+__global__ void __launch_bounds__(256) wgrad_reduce_scalar_kernel(const float* __restrict__ part, float* __restrict__ dw, int O,
+                                                                  int I, int k, int splits) {
+  const long long total = (long long)O * I * k * k;
+  const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / RL;
+  const int l = threadIdx.x % RL;
   float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += part[(long long)sp * total + idx];
-  dw[(((long long)o * I + i) * k + a) * k + b] = s;
+  if (idx < total)
+    for (int sp = l; sp < splits; sp += RL) s += __ldg(part + (long long)sp * total + idx);
+#pragma unroll
+  for (int o = RL / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (idx < total && l == 0) {
+    const int i = (int)(idx % I);
+    long long tt = idx / I;
+    const int b = (int)(tt % k);
+    tt /= k;
+    const int a = (int)(tt % k);
+    const int o = (int)(tt / k);
+    dw[(((long long)o * I + i) * k + a) * k + b] = s;
+  }
 }
 
 int launch_wgrad_reduce(const float* part, float* dw, int O, int I, int k, int splits, cudaStream_t st) {
@@ -926,7 +933,8 @@ int launch_wgrad_reduce(const float* part, float* dw, int O, int I, int k, int s
     if (splits >= 16) wgrad_reduce_vec_kernel<8><<<(unsigned)ceil_div64(groups * 8, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
     else wgrad_reduce_vec_kernel<1><<<(unsigned)ceil_div64(groups, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
   } else {
-    wgrad_reduce_scalar_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
+    if (splits >= 16) wgrad_reduce_scalar_kernel<32><<<(unsigned)ceil_div64(total * 32, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
+    else wgrad_reduce_scalar_kernel<1><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
   }
   SGK_LAUNCH_CHECK("wgrad_reduce_kernel");
   return SGK_OK;

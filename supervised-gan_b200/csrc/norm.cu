@@ -162,27 +162,51 @@ __global__ void norm_finalize_kernel(const float* __restrict__ x, const float* _
 }
 
 // ------------------------------------------------------------------------------ forward apply
+// Blocks own a (row chunk, column group, group) like the statistics pass, so every thread keeps the coefficients of its
+// V channels in registers: y = act((x - mean) * a + beta) with a = rstd*gamma (mean subtracted first: no cancellation
+// when |mean| >> std) -- one vector load, one vector store and 2V flops per element, no per-element statistics traffic.
 template <int V>
 __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                          const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, int C, long long rows_per_group,
-                                                         long long totalv, int act, float slope) {
+                                                         const float* __restrict__ beta, int C, int cols, int rlanes,
+                                                         long long rows, long long rows_per_chunk, int act, float slope) {
   const int CV = C / V;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += stride) {
-    long long row = i / CV;
-    int c = (int)(i - row * CV) * V;
-    int group = (int)(row / rows_per_group);
-    float v[V], r[V];
-    vload<V>(x + i * V, v);
-    const float* st = stats + ((long long)group * C + c) * 2;  // (mean, rstd) pairs
+  const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+  const int cv = blockIdx.y * cols + tc;
+  const int group = blockIdx.z, chunk = blockIdx.x;
+  if (cv >= CV) return;
+  float ca[V], cb[V], cm[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float t = (v[k] - __ldg(st + 2 * k)) * __ldg(st + 2 * k + 1);
-      if (gamma != nullptr) t = fmaf(t, __ldg(gamma + c + k), __ldg(beta + c + k));
-      r[k] = act_apply(t, act, slope);
+  for (int i = 0; i < V; ++i) {
+    const long long si = ((long long)group * C + cv * V + i) * 2;
+    const float mean = __ldg(stats + si), rstd = __ldg(stats + si + 1);
+    const float ga = gamma != nullptr ? __ldg(gamma + cv * V + i) : 1.f, be = gamma != nullptr ? __ldg(beta + cv * V + i) : 0.f;
+    ca[i] = rstd * ga;
+    cb[i] = be;
+    cm[i] = mean;
+  }
+  const float* __restrict__ xg = x + (long long)group * rows * C + cv * V;
+  float* __restrict__ yg = y + (long long)group * rows * C + cv * V;
+  long long r0 = (long long)chunk * rows_per_chunk, r1 = r0 + rows_per_chunk;
+  if (r1 > rows) r1 = rows;
+  long long r = r0 + tr;
+  for (; r + 3LL * rlanes < r1; r += 4LL * rlanes) {
+    float v[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) vload<V>(xg + (r + (long long)u * rlanes) * C, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[u][i] = act_apply(fmaf(v[u][i] - cm[i], ca[i], cb[i]), act, slope);
+      vstore<V>(yg + (r + (long long)u * rlanes) * C, v[u]);
     }
-    vstore<V>(y + i * V, r);
+  }
+  for (; r < r1; r += rlanes) {
+    float v[V];
+    vload<V>(xg + r * C, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = act_apply(fmaf(v[i] - cm[i], ca[i], cb[i]), act, slope);
+    vstore<V>(yg + r * C, v);
   }
 }
 
@@ -298,32 +322,66 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, float* 
   sums[idx * 2 + 1] = s2 * inv_n;
 }
 
+// dx = a1*g + a2*(x - mean) + a3 with g = dy * act'(a1*(x - mean) + beta); per-channel coefficients live in registers
+//   a1 = gamma*rstd, a2 = -gamma*rstd^2*m2, a3 = -gamma*rstd*m1
 template <int V>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                              const float* __restrict__ stats, const float* __restrict__ sums,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                             float* __restrict__ dx, int C, long long rows_per_group,
-                                                             long long totalv, int act, float slope) {
+                                                             float* __restrict__ dx, int C, int cols, int rlanes, long long rows,
+                                                             long long rows_per_chunk, int act, float slope) {
   const int CV = C / V;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += stride) {
-    long long row = i / CV;
-    int c = (int)(i - row * CV) * V;
-    int group = (int)(row / rows_per_group);
-    float xs[V], ds[V], r[V];
-    vload<V>(x + i * V, xs);
-    vload<V>(dy + i * V, ds);
+  const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+  const int cv = blockIdx.y * cols + tc;
+  const int group = blockIdx.z, chunk = blockIdx.x;
+  if (cv >= CV) return;
+  float a1[V], a2[V], a3[V], b1[V], b2[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      long long si = ((long long)group * C + c + k) * 2;
-      float mean = __ldg(stats + si), rstd = __ldg(stats + si + 1);
-      float m1 = __ldg(sums + si), m2 = __ldg(sums + si + 1);
-      float ga = gamma ? __ldg(gamma + c + k) : 1.f, be = gamma ? __ldg(beta + c + k) : 0.f;
-      float xh = (xs[k] - mean) * rstd;
-      float g = ds[k] * act_grad_pre(fmaf(xh, ga, be), act, slope);
-      r[k] = ga * rstd * (g - m1 - xh * m2);
+  for (int i = 0; i < V; ++i) {
+    const long long si = ((long long)group * C + cv * V + i) * 2;
+    const float mean = __ldg(stats + si), rstd = __ldg(stats + si + 1);
+    const float m1 = __ldg(sums + si), m2 = __ldg(sums + si + 1);
+    const float ga = gamma != nullptr ? __ldg(gamma + cv * V + i) : 1.f, be = gamma != nullptr ? __ldg(beta + cv * V + i) : 0.f;
+    a1[i] = ga * rstd;
+    a2[i] = -ga * rstd * rstd * m2;
+    a3[i] = -ga * rstd * m1;
+    b1[i] = mean;
+    b2[i] = be;
+  }
+  const long long base = (long long)group * rows * C + cv * V;
+  long long r0 = (long long)chunk * rows_per_chunk, r1 = r0 + rows_per_chunk;
+  if (r1 > rows) r1 = rows;
+  long long r = r0 + tr;
+  for (; r + (long long)rlanes < r1; r += 2LL * rlanes) {
+    float xv[2][V], dv[2][V];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      vload<V>(x + base + (r + (long long)u * rlanes) * C, xv[u]);
+      vload<V>(dy + base + (r + (long long)u * rlanes) * C, dv[u]);
     }
-    vstore<V>(dx + i * V, r);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xc = xv[u][i] - b1[i];
+        const float g = dv[u][i] * act_grad_pre(fmaf(xc, a1[i], b2[i]), act, slope);
+        o[i] = fmaf(a1[i], g, fmaf(a2[i], xc, a3[i]));
+      }
+      vstore<V>(dx + base + (r + (long long)u * rlanes) * C, o);
+    }
+  }
+  for (; r < r1; r += rlanes) {
+    float xv[V], dv[V], o[V];
+    vload<V>(x + base + r * C, xv);
+    vload<V>(dy + base + r * C, dv);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float xc = xv[i] - b1[i];
+      const float g = dv[i] * act_grad_pre(fmaf(xc, a1[i], b2[i]), act, slope);
+      o[i] = fmaf(a1[i], g, fmaf(a2[i], xc, a3[i]));
+    }
+    vstore<V>(dx + base + r * C, o);
   }
 }
 
@@ -375,12 +433,8 @@ extern "C" int sgk_norm_act_fwd(const float* x, float* y, float* stats, const fl
   norm_finalize_kernel<<<ceil_div(gc, 4), 128, 0, st>>>(x, part, stats, running_mean, running_var, momentum, eps, C,
                                                           g.rows, g.chunks, g.groups);
   SGK_LAUNCH_CHECK("norm_finalize_kernel");
-  long long total4 = (long long)N * H * W * g.C4;
-  long long blocks = ceil_div64(total4, 256 * 4);
-  long long cap = 16LL * sm_count();
-  if (blocks > cap) blocks = cap;
-  if (vec) norm_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, y, stats, gamma, beta, C, g.rows, total4, act, slope);
-  else norm_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, y, stats, gamma, beta, C, g.rows, total4, act, slope);
+  if (vec) norm_apply_kernel<4><<<grid, 256, 0, st>>>(x, y, stats, gamma, beta, C, g.cols, g.rlanes, g.rows, g.rows_per_chunk, act, slope);
+  else norm_apply_kernel<1><<<grid, 256, 0, st>>>(x, y, stats, gamma, beta, C, g.cols, g.rlanes, g.rows, g.rows_per_chunk, act, slope);
   SGK_LAUNCH_CHECK("norm_apply_kernel");
   return SGK_OK;
 }
@@ -408,12 +462,8 @@ extern "C" int sgk_norm_act_bwd(const float* dy, const float* x, const float* st
   int gc = g.groups * C;
   norm_bwd_finalize_kernel<<<ceil_div(gc, 4), 128, 0, st>>>(part, sums, dgamma, dbeta, C, g.rows, g.chunks, g.groups);
   SGK_LAUNCH_CHECK("norm_bwd_finalize_kernel");
-  long long total4 = (long long)N * H * W * g.C4;
-  long long blocks = ceil_div64(total4, 256 * 4);
-  long long cap = 16LL * sm_count();
-  if (blocks > cap) blocks = cap;
-  if (vec) norm_bwd_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(dy, x, stats, sums, gamma, beta, dx, C, g.rows, total4, act, slope);
-  else norm_bwd_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(dy, x, stats, sums, gamma, beta, dx, C, g.rows, total4, act, slope);
+  if (vec) norm_bwd_apply_kernel<4><<<grid, 256, 0, st>>>(dy, x, stats, sums, gamma, beta, dx, C, g.cols, g.rlanes, g.rows, g.rows_per_chunk, act, slope);
+  else norm_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(dy, x, stats, sums, gamma, beta, dx, C, g.cols, g.rlanes, g.rows, g.rows_per_chunk, act, slope);
   SGK_LAUNCH_CHECK("norm_bwd_apply_kernel");
   return SGK_OK;
 }
