@@ -376,6 +376,171 @@ conv_gather_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
 }
 
 // ================================================================================================
+// TMA-fed gather GEMM (default for Cg % 32 == 0): the activation operand is loaded by the TMA unit too.
+// An M tile is a TH x TW = 8 x 16 block of output pixels of one image (one sub-pixel phase); for tap (a,b) and channel
+// chunk c0 its 128 gathered rows are exactly ONE 4-D tensor box {32 ch, 16 px, 8 rows, 1 image} of the NHWC input at
+// (c0, x0*is + iox + b, y0*is + ioy + a, n) with traversal stride `is` -- out-of-bounds coordinates (conv padding,
+// ragged tiles) are zero-filled by the hardware, and the box lands in shared memory as 128 rows x 128 B in the
+// SWIZZLE_128B image tcgen05.mma wants.  One elected thread issues both loads of a k-block (activations + weights);
+// no LSU work, no address arithmetic, no proxy fences on the operand path, and the TMA queue keeps many boxes in flight.
+//   warps 0-3  epilogue only (TMEM -> registers -> bias/act -> smem transpose -> coalesced NHWC stores)
+//   warp 4     TMEM alloc; lane 0: TMA producer        warp 5   lane 0: MMA issuer
+// ================================================================================================
+constexpr int TT_H = 8, TT_W = 16;
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
+struct alignas(64) TmaMaps {
+  CUtensorMap w[4];  // packed weights per phase
+  CUtensorMap a;     // NHWC activations as {C, W, H, N}, box {32, 16*is, 8*is, 1}, traversal strides {1, is, is, 1}
+};
+struct TmaParams {
+  const float* bias;
+  float* out;
+  int N, Cg, Ho, Wo, Co;
+  int act;
+  float slope;
+  int nphase;
+  GatherPhase ph[4];
+  int tiles_x[4], tiles_y[4];
+  int BN, stages, tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 3)
+conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ TmaMaps maps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.BN * 128u;
+  const uint32_t bar_base = smem_base + (uint32_t)S * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (uint32_t)(2 * S);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+  int phi = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < p.nphase && (int)blockIdx.x >= p.ph[i].m_tile_begin) phi = i;
+  const GatherPhase P = p.ph[phi];
+  int t = (int)blockIdx.x - P.m_tile_begin;
+  const int per_img = p.tiles_x[phi] * p.tiles_y[phi];
+  const int n = t / per_img;
+  t -= n * per_img;
+  const int ty0 = (t / p.tiles_x[phi]) * TT_H, tx0 = (t % p.tiles_x[phi]) * TT_W;
+  const int n0 = blockIdx.y * p.BN;
+  const int cchunks = p.Cg >> 5;
+  const int KB = P.ta * P.tb * cchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);   // one arrive.expect_tx by the TMA thread (both boxes complete_tx on it)
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_acc;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    // =============================================================== epilogue
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t j = (uint32_t)(lane & 7);
+    const int rsub = lane >> 3;
+    const int r_own = warp * 32 + lane;
+    const uint32_t stg = smem_base;   // stage 0's A region is idle once the accumulator is complete
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    for (int cc = 0; cc < p.BN; cc += 32) {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + (uint32_t)cc, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cc + 4 * q));
+        const float o0 = act_apply(__uint_as_float(v[4 * q + 0]) + bv.x, p.act, p.slope);
+        const float o1 = act_apply(__uint_as_float(v[4 * q + 1]) + bv.y, p.act, p.slope);
+        const float o2 = act_apply(__uint_as_float(v[4 * q + 2]) + bv.z, p.act, p.slope);
+        const float o3 = act_apply(__uint_as_float(v[4 * q + 3]) + bv.w, p.act, p.slope);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r_own * 128u +
+                                                                    (((uint32_t)q ^ (uint32_t)(r_own & 7)) << 4)),
+                     "f"(o0), "f"(o1), "f"(o2), "f"(o3)
+                     : "memory");
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp * 32 + i * 4 + rsub;
+        const int oy = ty0 + r / TT_W, ox = tx0 + r % TT_W;
+        float4 o;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                     : "r"(stg + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
+        if (oy < P.Hp && ox < P.Wp) {
+          float* dstp = p.out + (((long long)n * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co + n0 + cc + 4 * j;
+          *reinterpret_cast<float4*>(dstp) = o;
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 4) {
+    // =============================================================== TMA producer (activations + weights)
+    if (lane == 0) {
+      const void* wmap = &maps.w[phi];
+      const uint32_t tx_bytes = (uint32_t)TC_A_BYTES + (uint32_t)p.BN * 128u;
+      const int x_base = tx0 * P.is + P.iox, y_base = ty0 * P.is + P.ioy;
+      int a = 0, b = 0, c0 = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % S;
+        mbar_wait(empty_bar(s), (uint32_t)(((kb / S) & 1) ^ 1));
+        mbar_arrive_expect_tx(full_bar(s), tx_bytes);
+        const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
+        tma_load_4d(abase, &maps.a, c0, x_base + b, y_base + a, n, full_bar(s));
+        tma_load_2d(abase + TC_A_BYTES, wmap, kb * 32, n0, full_bar(s));
+        c0 += 32;
+        if (c0 >= p.Cg) {
+          c0 = 0;
+          if (++b == P.tb) { b = 0; ++a; }
+        }
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % S;
+        mbar_wait(full_bar(s), (uint32_t)((kb / S) & 1));
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t b_addr = a_addr + TC_A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_tf32(tmem_acc, make_sw128_kmajor_desc(a_addr + kk * 32), make_sw128_kmajor_desc(b_addr + kk * 32), idesc,
+                    (uint32_t)((kb | kk) != 0));
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+}
+
+// ================================================================================================
 // Persistent variant of the gather GEMM (default).  One CTA per SM slot loops over (M tile, N tile) pairs with a
 // DOUBLE-BUFFERED accumulator in tensor memory, so the per-tile fixed costs (barrier set-up, TMEM allocation, first-load
 // latency, epilogue) overlap with the main loop of the neighbouring tiles instead of being paid 28 waves in a row:
@@ -749,6 +914,49 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   // The persistent variant overlaps per-tile fixed costs, but these gathers are bound by loads in flight per SM and the
   // non-persistent launch with up to 4 resident CTAs keeps more of them in flight (measured: 9.2 vs 9.45 ms of conv per
   // step); it stays available for experiments with SGK_TC_PERSIST=1.
+  // ---- TMA-fed variant: activations as 4-D tensor boxes (needs 32-channel chunks and full 32-column N tiles)
+  static const bool use_tma = !(getenv("SGK_TC_TMA") != nullptr && atoi(getenv("SGK_TC_TMA")) == 0);
+  if (use_tma && cs == 0 && BN >= 32) {
+    const int is = g.ph[0].is;
+    TmaParams q{};
+    TmaMaps tm{};
+    q.bias = bias; q.out = out;
+    q.N = g.N; q.Cg = g.Cg; q.Ho = g.Ho; q.Wo = g.Wo; q.Co = g.Co;
+    q.act = act; q.slope = slope; q.nphase = g.nphase;
+    q.BN = BN; q.tmem_cols = BN < 32 ? 32 : BN;
+    int tst = 4;
+    { const char* ev = getenv("SGK_TMA_STAGES"); if (ev) tst = atoi(ev); }
+    while (tst > 2 && (size_t)tst * stage_bytes > 72 * 1024) --tst;   // <= 72 KB of ring per CTA: 3 CTAs per SM
+    q.stages = tst;
+    long long mt = 0;
+    for (int i = 0; i < g.nphase; ++i) {
+      q.ph[i] = g.ph[i];
+      q.ph[i].m_tile_begin = (int)mt;
+      q.tiles_x[i] = ceil_div(g.ph[i].Wp, TT_W);
+      q.tiles_y[i] = ceil_div(g.ph[i].Hp, TT_H);
+      mt += (long long)g.N * q.tiles_x[i] * q.tiles_y[i];
+      tm.w[i] = maps.w[i];
+    }
+    if (mt > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return SGK_EUNSUPPORTED; }
+    cuuint64_t adim[4] = {(cuuint64_t)g.Cg, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+    cuuint64_t astr[3] = {(cuuint64_t)g.Cg * 4, (cuuint64_t)g.Wi * g.Cg * 4, (cuuint64_t)g.Hi * g.Wi * g.Cg * 4};
+    cuuint32_t abox[4] = {32u, (cuuint32_t)(TT_W * is), (cuuint32_t)(TT_H * is), 1u};
+    cuuint32_t aest[4] = {1u, (cuuint32_t)is, (cuuint32_t)is, 1u};
+    CUresult r = encode(&tm.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, adim, astr, abox, aest, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(activations) failed (%d)", (int)r); return SGK_ECUDA; }
+    const size_t tsmem = (size_t)tst * stage_bytes + 8 * (2 * tst + 2) + 1024;
+    static bool tattr = false;
+    if (!tattr) {
+      cudaError_t e = cudaFuncSetAttribute(conv_tma_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tma_tc_kernel)");
+      tattr = true;
+    }
+    dim3 tgrid((unsigned)mt, (unsigned)(g.Co / BN));
+    conv_tma_tc_kernel<<<tgrid, TC_THREADS, tsmem, st>>>(q, tm);
+    SGK_LAUNCH_CHECK("conv_tma_tc_kernel");
+    return SGK_OK;
+  }
   static const bool persist = getenv("SGK_TC_PERSIST") != nullptr && atoi(getenv("SGK_TC_PERSIST")) != 0;
   const int n_tiles_n = ceil_div(g.Co, BN);
   if (persist) {
