@@ -327,7 +327,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU")
-    ap.add_argument("--precision", default=os.environ.get("SGK_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("SGK_PRECISION", "tf32"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

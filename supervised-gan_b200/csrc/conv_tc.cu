@@ -1295,8 +1295,163 @@ conv_wgrad_tc_kernel(const __grid_constant__ WTcParams p, const __grid_constant_
   if (warp == 4) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
 }
 
+// ================================================================================================
+// TMA-fed weight gradient (default for Cx % 32 == 0): a stage is a 4 x 8 block of G-grid pixels of one image; the G tile
+// and, for each of the CTA's taps, the gathered X tile are 4-D tensor boxes ({32 ch, 8 px, 4 rows, 1 image}, X with the
+// conv stride as traversal stride and the tap offset in its coordinates), zero-filled out of bounds (padding, ragged
+// tiles: zero contribution), written in the SWIZZLE_128B_ATOM_32B image the MN-major tf32 MMA requires.
+// No producer warps: lane 0 of warp 4 issues all boxes of a stage onto one mbarrier.
+// ================================================================================================
+constexpr int WT_H = 4, WT_W = 8;   // 32 pixels per stage
+struct alignas(64) WTmaMaps {
+  CUtensorMap g;  // {Cm, Wg, Hg, N}, box {32, 8, 4, 1}
+  CUtensorMap x;  // {Cx, Wx, Hx, N}, box {32, 8*s, 4*s, 1}, traversal strides {1, s, s, 1}
+};
+struct WTmaParams {
+  float* part;
+  int Cm, Cx, k, s, off, K;
+  int tiles_x, tiles_y;          // per image
+  long long T, t_per_split;      // pixel tiles in total / per split
+  int TT, Nc, tmem_cols, stages;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 3)
+conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constant__ WTmaMaps maps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const int ncg = p.Nc >> 5;
+  const uint32_t b_bytes = (uint32_t)p.TT * (uint32_t)ncg * WTC_BLK;
+  const uint32_t stage_bytes = WTC_A_BYTES + b_bytes;
+  const uint32_t bar_base = smem_base + S * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (uint32_t)(2 * S);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+  const int ctiles = p.Cx / p.Nc;
+  const int t0 = ((int)blockIdx.x / ctiles) * p.TT;
+  const int c0 = ((int)blockIdx.x % ctiles) * p.Nc;
+  const int mch0 = blockIdx.y * 128;
+  const long long tbeg = (long long)blockIdx.z * p.t_per_split;
+  long long tend = tbeg + p.t_per_split;
+  if (tend > p.T) tend = p.T;
+  const int steps = tend > tbeg ? (int)(tend - tbeg) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_acc;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    // =============================================================== epilogue: lane = out channel m; columns = (tap, c)
+    if (steps > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const int r_own = warp * 32 + lane;
+    const int rsub = lane >> 3;
+    const uint32_t j = (uint32_t)(lane & 7);
+    const uint32_t stg = smem_base;
+    float* __restrict__ pbase = p.part + (long long)blockIdx.z * p.Cm * p.K;
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    const int ncols = p.TT * p.Nc;
+    for (int cc = 0; cc < ncols; cc += 32) {
+      uint32_t v[32];
+      if (steps > 0) {
+        tmem_ld32(lane_addr + (uint32_t)cc, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r_own * 128u +
+                                                                    (((uint32_t)q ^ (uint32_t)(r_own & 7)) << 4)),
+                     "r"(v[4 * q]), "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                     : "memory");
+      __syncwarp();
+      const int ti = cc / p.Nc, cin = cc - ti * p.Nc;
+      const long long colofs = (long long)(t0 + ti) * p.Cx + c0 + cin + 4 * j;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp * 32 + i * 4 + rsub;
+        const int m = mch0 + r;
+        float4 o;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                     : "r"(stg + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
+        if (m < p.Cm) *reinterpret_cast<float4*>(pbase + (long long)m * p.K + colofs) = o;
+      }
+      __syncwarp();
+    }
+  } else if (warp == 4) {
+    // =============================================================== TMA producer: G tile + TT gathered X tiles per stage
+    if (lane == 0) {
+      const int per_img = p.tiles_x * p.tiles_y;
+      const uint32_t tx_bytes = WTC_A_BYTES + b_bytes;
+      for (int st = 0; st < steps; ++st) {
+        const int s = st % S;
+        mbar_wait(empty_bar(s), (uint32_t)(((st / S) & 1) ^ 1));
+        mbar_arrive_expect_tx(full_bar(s), tx_bytes);
+        const long long t = tbeg + st;
+        const int n = (int)(t / per_img);
+        const int r2 = (int)(t - (long long)n * per_img);
+        const int ty0 = (r2 / p.tiles_x) * WT_H, tx0 = (r2 % p.tiles_x) * WT_W;
+        const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) tma_load_4d(abase + g4 * WTC_BLK, &maps.g, mch0 + g4 * 32, tx0, ty0, n, full_bar(s));
+        const uint32_t bbase = abase + WTC_A_BYTES;
+        for (int ti = 0; ti < p.TT; ++ti) {
+          const int tap = t0 + ti;
+          const int a = tap / p.k, b = tap - a * p.k;
+          for (int cg = 0; cg < ncg; ++cg)
+            tma_load_4d(bbase + (uint32_t)(ti * ncg + cg) * WTC_BLK, &maps.x, c0 + cg * 32, tx0 * p.s + b + p.off,
+                        ty0 * p.s + a + p.off, n, full_bar(s));
+        }
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32_mn(128, p.Nc);
+      for (int st = 0; st < steps; ++st) {
+        const int s = st % S;
+        mbar_wait(full_bar(s), (uint32_t)((st / S) & 1));
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t b_addr = a_addr + WTC_A_BYTES;
+        for (int ti = 0; ti < p.TT; ++ti) {
+#pragma unroll
+          for (int kg = 0; kg < 4; ++kg)
+            umma_tf32(tmem_acc + (uint32_t)(ti * p.Nc), make_sw128b32_mnmajor_desc(a_addr + kg * 1024, WTC_BLK, 512u),
+                      make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(ti * ncg) * WTC_BLK + kg * 1024, WTC_BLK, 512u), idesc,
+                      (uint32_t)((st | kg) != 0));
+        }
+        umma_commit(empty_bar(s));
+      }
+      if (steps > 0) umma_commit(tmem_full_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+}
+
 // plan shared by the workspace query and the launch
-struct WTcPlan { int ok, TT, Nc, tmem_cols, splits, cs, ctiles; long long pps; };
+struct WTcPlan { int ok, TT, Nc, tmem_cols, splits, cs, ctiles, tma, tiles_x, tiles_y; long long pps, T, tps; };
 static WTcPlan wgrad_tc_plan(const EquivConv& e) {
   WTcPlan w{};
   if ((e.O % 4) != 0) return w;                 // the G tile is a TMA box: row stride must be a multiple of 16 B
@@ -1333,6 +1488,21 @@ static WTcPlan wgrad_tc_plan(const EquivConv& e) {
   if (s > 256) s = 256;
   w.pps = ceil_div64(ceil_div64(P, s), WTC_P) * WTC_P;
   w.splits = (int)ceil_div64(P, w.pps);
+  static const bool use_tma = !(getenv("SGK_WTMA") != nullptr && atoi(getenv("SGK_WTMA")) == 0);
+  w.tma = (use_tma && w.cs == 0) ? 1 : 0;
+  if (w.tma) {
+    // pixels are walked as 4 x 8 tiles per image; splits are ranges of tiles
+    w.tiles_x = ceil_div(e.Ws, WT_W);
+    w.tiles_y = ceil_div(e.Hs, WT_H);
+    w.T = (long long)e.N * w.tiles_x * w.tiles_y;
+    long long sp = ceil_div64(2LL * 3 * sm_count(), tiles);
+    long long maxsp = ceil_div64(w.T, 8);
+    if (sp > maxsp) sp = maxsp;
+    if (sp < 1) sp = 1;
+    if (sp > 256) sp = 256;
+    w.tps = ceil_div64(w.T, sp);
+    w.splits = (int)ceil_div64(w.T, w.tps);
+  }
   w.ok = 1;
   return w;
 }
@@ -1366,6 +1536,42 @@ int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* 
   p.P = (long long)e.N * e.Hs * e.Ws; p.p_per_split = w.pps;
   p.TT = w.TT; p.Nc = w.Nc; p.tmem_cols = w.tmem_cols;
   p.cs = w.cs; p.Kflat = e.k * e.k * e.I;
+  if (w.tma) {
+    WTmaParams q{};
+    WTmaMaps tm{};
+    q.part = (float*)ws;
+    q.Cm = e.O; q.Cx = e.I; q.k = e.k; q.s = e.s; q.off = -e.p; q.K = e.k * e.k * e.I;
+    q.tiles_x = w.tiles_x; q.tiles_y = w.tiles_y; q.T = w.T; q.t_per_split = w.tps;
+    q.TT = w.TT; q.Nc = w.Nc; q.tmem_cols = w.tmem_cols;
+    static const int wst = getenv("SGK_WTMA_STAGES") ? atoi(getenv("SGK_WTMA_STAGES")) : 2;
+    q.stages = wst < 2 ? 2 : (wst > 4 ? 4 : wst);
+    cuuint64_t gd[4] = {(cuuint64_t)e.O, (cuuint64_t)e.Ws, (cuuint64_t)e.Hs, (cuuint64_t)e.N};
+    cuuint64_t gs[3] = {(cuuint64_t)e.O * 4, (cuuint64_t)e.Ws * e.O * 4, (cuuint64_t)e.Hs * e.Ws * e.O * 4};
+    cuuint32_t gb[4] = {32u, (cuuint32_t)WT_W, (cuuint32_t)WT_H, 1u};
+    cuuint32_t ge[4] = {1u, 1u, 1u, 1u};
+    CUresult r1 = encode(&tm.g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g, gd, gs, gb, ge, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint64_t xd[4] = {(cuuint64_t)e.I, (cuuint64_t)e.Wb, (cuuint64_t)e.Hb, (cuuint64_t)e.N};
+    cuuint64_t xs[3] = {(cuuint64_t)e.I * 4, (cuuint64_t)e.Wb * e.I * 4, (cuuint64_t)e.Hb * e.Wb * e.I * 4};
+    cuuint32_t xb[4] = {32u, (cuuint32_t)(WT_W * e.s), (cuuint32_t)(WT_H * e.s), 1u};
+    cuuint32_t xe[4] = {1u, (cuuint32_t)e.s, (cuuint32_t)e.s, 1u};
+    CUresult r2 = encode(&tm.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.x, xd, xs, xb, xe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(wgrad) failed (%d, %d)", (int)r1, (int)r2); return SGK_ECUDA; }
+    const uint32_t stb = WTC_A_BYTES + (uint32_t)w.TT * (w.Nc / 32) * WTC_BLK;
+    while (q.stages > 2 && (size_t)q.stages * stb > 190 * 1024) --q.stages;
+    const size_t smem2 = (size_t)q.stages * stb + 8 * (2 * q.stages + 2) + 1024;
+    static bool tattr = false;
+    if (!tattr) {
+      cudaError_t ce = cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(conv_wgrad_tma_kernel)");
+      tattr = true;
+    }
+    dim3 grid2((unsigned)w.ctiles, (unsigned)ceil_div(e.O, 128), (unsigned)w.splits);
+    conv_wgrad_tma_kernel<<<grid2, TC_THREADS, smem2, st>>>(q, tm);
+    SGK_LAUNCH_CHECK("conv_wgrad_tma_kernel");
+    return launch_wgrad_reduce((const float*)ws, dw, e.O, e.I, e.k, w.splits, st);
+  }
   cuuint64_t gdim[2] = {(cuuint64_t)e.O, (cuuint64_t)p.P};
   cuuint64_t gstr[1] = {(cuuint64_t)e.O * sizeof(float)};
   cuuint32_t box[2] = {32u, (cuuint32_t)WTC_P};
