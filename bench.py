@@ -221,6 +221,7 @@ def run_ours(args):
     # ---------------- timed region 2: end to end through the public API, H2D + D2H inside.  The model replays its own
     # captured step graph (opt.cuda_graph, the documented fast path of the public API); set_input copies into the
     # captured input buffer.
+    used_graph = graph is not None
     if graph is not None:
         graph = None                      # drop the bench-level graph; the model captures its own below
         m.use_graph = True
@@ -272,7 +273,9 @@ def run_ours(args):
         for tag, e in summ.items():
             f = fam.setdefault(tag.split(" ")[0], {"ms": 0.0, "flops": 0.0, "launches": 0})
             f["ms"] += e["ms"]; f["flops"] += e["flops"]; f["launches"] += e["launches"]
-        top_tag, top = max(summ.items(), key=lambda kv: kv[1]["ms"])
+        byk = timer.summary(by="kernel")
+        top_tag, top = max(byk.items(), key=lambda kv: kv[1]["ms"])
+        top_layer, top_l = max(((t, e) for t, e in summ.items()), key=lambda kv: kv[1]["ms"])
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -282,7 +285,11 @@ def run_ours(args):
         ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
         conv_ms = sum(f["ms"] for f in fam.values()) / 2.0
         roof = {"bound": "tensor", "kernel": top_tag, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None,
+                "traffic": None, "launches_per_step": top["launches"] // 2, "ms_per_step": top["ms"] / 2.0,
+                "by_kernel": {k: {"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "ms_per_step": v["ms"] / 2.0,
+                                  "launches_per_step": v["launches"] // 2} for k, v in sorted(byk.items(), key=lambda kv: -kv[1]["ms"])},
+                "slowest_layer": {"layer": top_layer, "ms": top_l["ms"] / top_l["launches"],
+                                  "tflops": top_l["flops"] / (top_l["ms"] * 1e-3) / 1e12},
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
                 "conv_families": {k: {"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "ms_per_step": v["ms"] / 2.0,
                                       "launches_per_step": v["launches"] // 2} for k, v in fam.items()},
@@ -302,7 +309,7 @@ def run_ours(args):
                 "config": {"workload": "fcgan 512x512 G+D step (BASELINE configs[3]): deconv G n_layers 5 ngf 32 noise 8x8x8 + "
                                        "3-scale n_layers D ndf 32 scale 1/2/4, instance norm, BCE, 2 channels, pool_size 0",
                            "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                           "cuda_graph": graph is not None,
+                           "cuda_graph": used_graph,
                            "l2": "inputs larger than L2: the step streams > 1 GB of activations per replay (126 MB L2), no flush"},
                 "clocks": clk, "gpu_launches": int(gpu_launches),
                 "e2e": {"value": B * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -76,6 +76,11 @@ int sgk_version(void);
 const char* sgk_last_error(void);
 /* total kernels this library has launched (or captured into a graph) in this process so far */
 long long sgk_launch_count(void);
+/* diagnostics: while on, the calling thread records the names of the kernels this library launches; sgk_traced_kernels
+ * returns them joined by '+' (at most 511 chars) and clears the record.  bench.py uses it to attribute per-launch timings
+ * to kernels (the reference has no counterpart: torch.profiler would play this role around networks.py forward calls). */
+void sgk_trace_kernels(int on);
+const char* sgk_traced_kernels(void);
 /* number of SMs / compute capability of the current device (sanity check by the host side) */
 int sgk_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -129,6 +134,21 @@ int sgk_act_fwd(const float* x, float* y, size_t n, int act, float slope, void* 
 /* db[c] = sum over rows of dy[rows, C] (NHWC bias gradient) */
 int sgk_bias_grad(const float* dy, float* db, size_t rows, int C, void* workspace, size_t workspace_bytes, void* stream);
 size_t sgk_bias_grad_workspace_bytes(size_t rows, int C);
+/* Tap folding for thin-output stride-1 convs -- the PatchGAN logit head Conv2d(ndf*8, 1, kw=4, stride=1, padding=2)
+ * (networks.py:835) and its autograd.  With Cout*k*k <= sgk_tap_rows() (32) the layer is evaluated as a 1x1 conv
+ * t = x . W32^T (x read once; sgk_conv_* with k=1 on the tensor-core path) followed by a fold over the k*k taps:
+ *   y[n,oy,ox,co] = act(bias[co] + sum_{a,b} t[n, oy+a-p, ox+b-p, (co*k+a)*k+b]).
+ * Backward: G32 = unfold(dy) per input pixel, dx / dW32 = dgrad / wgrad of the 1x1 conv, dW = unpack(dW32).
+ *   sgk_tap_weight_pack   : w[Cout][Cin][k][k] -> W32[32][Cin] (rows >= Cout*k*k zero)
+ *   sgk_tap_weight_unpack : dW32[32][Cin] -> dw[Cout][Cin][k][k]
+ *   sgk_tap_fold_fwd      : t[N,H,W,32] -> y[N,H+2p-k+1,W+2p-k+1,Cout]
+ *   sgk_tap_unfold        : dy[N,Ho,Wo,Cout] -> G32[N,H,W,32] */
+int sgk_tap_rows(void);
+int sgk_tap_weight_pack(const float* w, float* w32, int Cout, int Cin, int k, void* stream);
+int sgk_tap_weight_unpack(const float* dw32, float* dw, int Cout, int Cin, int k, void* stream);
+int sgk_tap_fold_fwd(const float* t, const float* bias, float* y, int N, int H, int W, int Cout, int k, int pad, int act,
+                     float slope, void* stream);
+int sgk_tap_unfold(const float* dy, float* g32, int N, int H, int W, int Cout, int k, int pad, void* stream);
 /* channel concat / split in NHWC (networks.py:417-419 U-Net skips, 713-733 CRN; cgan_model.py:162) */
 int sgk_concat2_nhwc(const float* a, int Ca, const float* b, int Cb, float* out, size_t pixels, void* stream);
 int sgk_split2_nhwc(const float* in, float* a, int Ca, float* b, int Cb, size_t pixels, void* stream);

@@ -32,6 +32,8 @@ SIGNATURES = {
     "sgk_version": (c_int, []),
     "sgk_last_error": (c_char_p, []),
     "sgk_launch_count": (ctypes.c_longlong, []),
+    "sgk_trace_kernels": (None, [ctypes.c_int]),
+    "sgk_traced_kernels": (ctypes.c_char_p, []),
     "sgk_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "sgk_conv_packed_weight_elems": (c_size_t, [POINTER(SgkConvDesc), c_int]),
     "sgk_conv_pack_weight": (c_int, [POINTER(SgkConvDesc), c_int, P, P, P]),
@@ -49,6 +51,11 @@ SIGNATURES = {
     "sgk_act_fwd": (c_int, [P, P, c_size_t, c_int, c_float, P]),
     "sgk_bias_grad": (c_int, [P, P, c_size_t, c_int, P, c_size_t, P]),
     "sgk_bias_grad_workspace_bytes": (c_size_t, [c_size_t, c_int]),
+    "sgk_tap_rows": (c_int, []),
+    "sgk_tap_weight_pack": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "sgk_tap_weight_unpack": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "sgk_tap_fold_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
+    "sgk_tap_unfold": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "sgk_concat2_nhwc": (c_int, [P, c_int, P, c_int, P, c_size_t, P]),
     "sgk_split2_nhwc": (c_int, [P, P, c_int, P, c_int, c_size_t, P]),
     "sgk_axpy": (c_int, [P, P, c_float, P, c_size_t, P]),

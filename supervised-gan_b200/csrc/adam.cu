@@ -94,7 +94,7 @@ extern "C" int sgk_adam_multi_tensor(const SgkAdamTensor* tensors_host, int n_te
     adam_kernel<<<nb, ADAM_THREADS, 0, st>>>(L, step_dev, hyper_dev);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return cuda_fail(e, "adam_kernel");
-    count_launch();
+    count_launch("adam_kernel");
     nt = 0; nb = 0;
     return SGK_OK;
   };
@@ -152,7 +152,7 @@ static int bucket_copy(float* const* ptrs, const int64_t* sizes, int n_tensors, 
     bucket_copy_kernel<PACK><<<nb, ADAM_THREADS, 0, st>>>(L, flat);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return cuda_fail(e, "bucket_copy_kernel");
-    count_launch();
+    count_launch("bucket_copy_kernel");
     nt = 0; nb = 0;
     return SGK_OK;
   };

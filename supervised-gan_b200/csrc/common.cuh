@@ -25,12 +25,12 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 // every kernel launch of the library goes through this: error check + launch accounting (sgk_launch_count)
-void count_launch();
+void count_launch(const char* what);
 #define SGK_LAUNCH_CHECK(what)                                   \
   do {                                                           \
     cudaError_t _e = cudaPeekAtLastError();                      \
     if (_e != cudaSuccess) return sgk::cuda_fail(_e, what);      \
-    sgk::count_launch();                                         \
+    sgk::count_launch(what);                                     \
   } while (0)
 
 int sm_count();

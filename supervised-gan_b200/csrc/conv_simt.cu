@@ -449,7 +449,7 @@ static bool try_launch_thin_transposed(const GatherPlan& g, const FParams& p, cu
   if (e != cudaSuccess) { *rc = cuda_fail(e, "cudaFuncSetAttribute(gather_thin_transposed_tile)"); return true; }
   e = cudaPeekAtLastError();
   if (e != cudaSuccess) { *rc = cuda_fail(e, "gather_thin_transposed_tile"); return true; }
-  count_launch();
+  count_launch("gather_thin_transposed_tile");
   *rc = SGK_OK;
   return true;
 }
@@ -545,7 +545,7 @@ static bool try_launch_edge_direct(const GatherPlan& g, const FParams& p, cudaSt
   }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { *rc = cuda_fail(e, "edge_direct_kernel"); return true; }
-  count_launch();
+  count_launch("edge_direct_kernel");
   *rc = SGK_OK;
   return true;
 }

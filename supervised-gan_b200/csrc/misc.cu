@@ -2,6 +2,7 @@
 // layout conversion at the network edges, standalone activations, bias gradient, NHWC concat/split.
 #include "common.cuh"
 #include <atomic>
+#include <cstring>
 
 namespace sgk {
 
@@ -20,7 +21,22 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 static std::atomic<long long> g_launches{0};
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// optional per-thread trace of kernel names (bench.py attributes its per-launch timings to kernels with it)
+static thread_local bool t_trace = false;
+static thread_local char t_trace_buf[512];
+static thread_local size_t t_trace_len = 0;
+void count_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (t_trace && what != nullptr) {
+    size_t n = strlen(what);
+    if (t_trace_len + n + 2 < sizeof(t_trace_buf)) {
+      if (t_trace_len) t_trace_buf[t_trace_len++] = '+';
+      memcpy(t_trace_buf + t_trace_len, what, n);
+      t_trace_len += n;
+      t_trace_buf[t_trace_len] = 0;
+    }
+  }
+}
 
 int sm_count() {
   static int cached[64] = {0};
@@ -174,6 +190,18 @@ using namespace sgk;
 extern "C" int sgk_version(void) { return SGK_VERSION; }
 extern "C" long long sgk_launch_count(void) { return sgk::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* sgk_last_error(void) { return sgk::g_err; }
+extern "C" void sgk_trace_kernels(int on) {
+  sgk::t_trace = on != 0;
+  sgk::t_trace_len = 0;
+  sgk::t_trace_buf[0] = 0;
+}
+extern "C" const char* sgk_traced_kernels(void) {
+  static thread_local char out[512];
+  memcpy(out, sgk::t_trace_buf, sizeof(out));
+  sgk::t_trace_len = 0;
+  sgk::t_trace_buf[0] = 0;
+  return out;
+}
 extern "C" int sgk_device_info(int* sm, int* major, int* minor) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

@@ -6,6 +6,7 @@ with the reference's nn.Modules.  PyTorch is used for device memory (caching all
 and the autograd graph only -- all arithmetic is in the .so; there is no CPU / ATen fallback.
 """
 import ctypes
+import os
 
 import torch
 
@@ -13,6 +14,7 @@ from . import _lib as L
 
 _precision = L.FP32
 _weights_epoch = 0
+_tap_fold = os.environ.get("SGK_TAP_FOLD", "1") != "0"   # tap-folded thin heads on the tensor-core paths (csrc/taps.cu)
 
 
 def set_precision(name):
@@ -44,18 +46,29 @@ class KernelTimer:
         self.records = []
 
     def time(self, tag, flops, fn):
+        lib = L.load()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lib.sgk_trace_kernels(1)          # per-thread: backward calls arrive on the autograd engine's thread
         a.record()
         rc = fn()
         b.record()
-        self.records.append((tag, flops, a, b))
+        kern = (lib.sgk_traced_kernels() or b"").decode()
+        lib.sgk_trace_kernels(0)
+        self.records.append((tag, flops, a, b, kern))
         return rc
 
-    def summary(self):
+    def summary(self, by="tag"):
+        """by='tag': per layer and pass; by='kernel': per main kernel (first kernel each call launched)."""
         torch.cuda.synchronize()
         out = {}
-        for tag, flops, a, b in self.records:
-            e = out.setdefault(tag, {"launches": 0, "ms": 0.0, "flops": 0.0})
+        for tag, flops, a, b, kern in self.records:
+            if by == "tag":
+                key = tag
+            else:
+                names = [k for k in kern.split("+") if k]
+                main = [k for k in names if k.startswith(("conv_", "gather_", "edge_", "pixel_reduce"))]
+                key = (main or names or ["?"])[0]
+            e = out.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0})
             e["launches"] += 1
             e["ms"] += a.elapsed_time(b)
             e["flops"] += flops
@@ -138,6 +151,35 @@ class ConvCfg:
         self._packed[op] = (tag, buf)
         return buf
 
+    # ---- tap-folded evaluation of thin-output stride-1 convs (csrc/taps.cu): Cout*k*k <= 32 rows of a 1x1 conv
+    def tap_folded(self, weight, x_shape):
+        if self.transposed or self.stride != 1 or self.k == 1 or _precision == L.FP32 or not _tap_fold:
+            return False
+        cout, cin = weight.shape[0], weight.shape[1]
+        return cout * self.k * self.k <= 32 and cin % 32 == 0
+
+    def tap_weights(self, weight, x_shape):
+        """(desc of the 1x1 conv, W32, packed fwd weight, packed dgrad weight), cached per weight version."""
+        lib = L.load()
+        N, H, W, C = x_shape
+        cout, cin = weight.shape[0], weight.shape[1]
+        desc1 = L.SgkConvDesc(N, cin, H, W, 32, H, W, 1, 1, 0, 0, _precision)
+        tag = (weight._version, _weights_epoch, weight.data_ptr(), _precision)
+        ent = self._packed.get("tap")
+        if ent is None or ent[0] != tag:
+            st = _stream()
+            w32 = ent[1] if ent is not None else torch.empty(32, cin, dtype=torch.float32, device=weight.device)
+            L.check(lib.sgk_tap_weight_pack(_p(weight), _p(w32), cout, cin, self.k, st), "tap_weight_pack")
+            bufs = []
+            for i, op in enumerate((L.OP_FWD, L.OP_DGRAD)):
+                n = lib.sgk_conv_packed_weight_elems(ctypes.byref(desc1), op)
+                buf = ent[2 + i] if ent is not None else torch.empty(n, dtype=torch.float32, device=weight.device)
+                L.check(lib.sgk_conv_pack_weight(ctypes.byref(desc1), op, _p(w32), _p(buf), st), "conv_pack_weight")
+                bufs.append(buf)
+            ent = (tag, w32, bufs[0], bufs[1])
+            self._packed["tap"] = ent
+        return desc1, ent[1], ent[2], ent[3]
+
 
 class _ConvFn(torch.autograd.Function):
     @staticmethod
@@ -148,9 +190,19 @@ class _ConvFn(torch.autograd.Function):
         b = _chk(bias.detach(), "conv bias") if bias is not None else None
         desc = cfg.desc(x.shape, w)
         y = torch.empty((desc.N, desc.Hout, desc.Wout, desc.Cout), dtype=torch.float32, device=x.device)
-        wp = cfg.packed(weight, desc, L.OP_FWD)
-        L.check(_timed(_conv_tag("fwd", desc), _conv_flops(desc), lambda: lib.sgk_conv_fwd(
-            ctypes.byref(desc), _p(x), _p(wp), _p(b), _p(y), act, slope, _stream())), "conv_fwd")
+        ctx.tap = cfg.tap_folded(w, x.shape)
+        if ctx.tap:
+            st = _stream()
+            desc1, _, wp1, _ = cfg.tap_weights(w, x.shape)
+            t = torch.empty((desc.N, desc.Hin, desc.Win, 32), dtype=torch.float32, device=x.device)
+            L.check(_timed(_conv_tag("fwd", desc1), _conv_flops(desc1), lambda: lib.sgk_conv_fwd(
+                ctypes.byref(desc1), _p(x), _p(wp1), None, _p(t), L.ACT_NONE, 0.0, st)), "conv_fwd(tap 1x1)")
+            L.check(lib.sgk_tap_fold_fwd(_p(t), _p(b), _p(y), desc.N, desc.Hin, desc.Win, desc.Cout, desc.k, desc.pad, act,
+                                         slope, st), "tap_fold_fwd")
+        else:
+            wp = cfg.packed(weight, desc, L.OP_FWD)
+            L.check(_timed(_conv_tag("fwd", desc), _conv_flops(desc), lambda: lib.sgk_conv_fwd(
+                ctypes.byref(desc), _p(x), _p(wp), _p(b), _p(y), act, slope, _stream())), "conv_fwd")
         ctx.cfg, ctx.desc, ctx.has_bias = cfg, desc, bias is not None
         # a conv bias that feeds an Instance/BatchNorm has an exactly-zero gradient (the norm removes the mean);
         # we emit exact zeros instead of the reference's ~1e-9 rounding noise (DESIGN.md "deviations")
@@ -172,6 +224,30 @@ class _ConvFn(torch.autograd.Function):
             L.check(lib.sgk_act_bwd(_p(dy), _p(y), _p(dpre), dy.numel(), ctx.act, ctx.slope, st), "act_bwd")
             dy = dpre
         gx = gw = gb = None
+        if ctx.tap:
+            desc1, _, _, wpd = cfg.tap_weights(weight.detach(), x.shape)
+            g32 = torch.empty((desc.N, desc.Hin, desc.Win, 32), dtype=torch.float32, device=dy.device)
+            L.check(lib.sgk_tap_unfold(_p(dy), _p(g32), desc.N, desc.Hin, desc.Win, desc.Cout, desc.k, desc.pad, st), "tap_unfold")
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                L.check(_timed(_conv_tag("dgrad", desc1), _conv_flops(desc1), lambda: lib.sgk_conv_dgrad(
+                    ctypes.byref(desc1), _p(g32), _p(wpd), _p(gx), st)), "conv_dgrad(tap 1x1)")
+            if ctx.needs_input_grad[1]:
+                gw = torch.empty_like(weight)
+                dw32 = torch.empty((32, desc.Cin), dtype=torch.float32, device=dy.device)
+                ws = _ws(lib.sgk_conv_wgrad_workspace_bytes(ctypes.byref(desc1)), dy.device)
+                L.check(_timed(_conv_tag("wgrad", desc1), _conv_flops(desc1), lambda: lib.sgk_conv_wgrad(
+                    ctypes.byref(desc1), _p(x), _p(g32), _p(dw32), None, _p(ws), ws.numel(), st)), "conv_wgrad(tap 1x1)")
+                L.check(lib.sgk_tap_weight_unpack(_p(dw32), _p(gw), desc.Cout, desc.Cin, desc.k, st), "tap_weight_unpack")
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                if ctx.bias_grad_zero:
+                    gb = torch.zeros(desc.Cout, dtype=torch.float32, device=dy.device)
+                else:
+                    gb = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device)
+                    rows = dy.numel() // desc.Cout
+                    ws = _ws(lib.sgk_bias_grad_workspace_bytes(rows, desc.Cout), dy.device)
+                    L.check(lib.sgk_bias_grad(_p(dy), _p(gb), rows, desc.Cout, _p(ws), ws.numel(), st), "bias_grad")
+            return gx, gw, gb, None, None, None, None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             wp = cfg.packed(weight, desc, L.OP_DGRAD)
