@@ -149,6 +149,10 @@ int sgk_tap_weight_unpack(const float* dw32, float* dw, int Cout, int Cin, int k
 int sgk_tap_fold_fwd(const float* t, const float* bias, float* y, int N, int H, int W, int Cout, int k, int pad, int act,
                      float slope, void* stream);
 int sgk_tap_unfold(const float* dy, float* g32, int N, int H, int W, int Cout, int k, int pad, void* stream);
+/* y[N,H+2p,W+2p,C] = zero-padded copy of x[N,H,W,C].  Image layers (2-channel input of the discriminator's first
+ * Conv2d(input_nc, ndf, kw=4, stride=2, padding=2), networks.py:815-818) are convolved from the padded copy with pad=0 so
+ * that the tensor-core path can fetch whole im2col tiles with one TMA box. */
+int sgk_pad_nhwc(const float* x, float* y, int N, int H, int W, int C, int pad, void* stream);
 /* channel concat / split in NHWC (networks.py:417-419 U-Net skips, 713-733 CRN; cgan_model.py:162) */
 int sgk_concat2_nhwc(const float* a, int Ca, const float* b, int Cb, float* out, size_t pixels, void* stream);
 int sgk_split2_nhwc(const float* in, float* a, int Ca, float* b, int Cb, size_t pixels, void* stream);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "sgk_tap_weight_unpack": (c_int, [P, P, c_int, c_int, c_int, P]),
     "sgk_tap_fold_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "sgk_tap_unfold": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "sgk_pad_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "sgk_concat2_nhwc": (c_int, [P, c_int, P, c_int, P, c_size_t, P]),
     "sgk_split2_nhwc": (c_int, [P, P, c_int, P, c_int, c_size_t, P]),
     "sgk_axpy": (c_int, [P, P, c_float, P, c_size_t, P]),

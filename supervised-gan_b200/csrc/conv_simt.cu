@@ -988,6 +988,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
 int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t st);
 size_t conv_wgrad_tc_workspace_bytes(const SgkConvDesc* d);
+int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* part, int ctas, cudaStream_t st);
 }
 
 static int conv_gather_dispatch(const SgkConvDesc* d, int op, const float* in, const float* w, const float* bias,
@@ -1022,7 +1023,7 @@ extern "C" size_t sgk_conv_wgrad_workspace_bytes(const SgkConvDesc* d) {
   size_t a = (size_t)splits * e.O * e.I * e.k * e.k * sizeof(float);
   size_t b = sgk_bias_grad_workspace_bytes((size_t)d->N * d->Hout * d->Wout, d->Cout);
   size_t c = d->precision != SGK_FP32 ? conv_wgrad_tc_workspace_bytes(d) : 0;
-  size_t dd = (size_t)2 * sm_count() * e.O * e.I * e.k * e.k * sizeof(float);   // image-edge kernel: one partial per CTA
+  size_t dd = (size_t)3 * sm_count() * e.O * e.I * e.k * e.k * sizeof(float);   // image-edge kernels: one partial per CTA
   a = a > b ? a : b;
   a = a > c ? a : c;
   return a > dd ? a : dd;
@@ -1050,7 +1051,7 @@ extern "C" int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float*
     const int tiles_x = ceil_div(e.Ws, EG_TW), tiles_y = ceil_div(e.Hs, EG_TH);
     long long ntiles = (long long)tiles_x * tiles_y * e.N;
     const int cgroups = ceil_div(e.O, 32);
-    long long ctas = 2LL * sm_count() / cgroups;
+    long long ctas = (ekey == 408 ? 3LL : 2LL) * sm_count() / cgroups;
     if (ctas < 1) ctas = 1;
     if (ctas > ntiles) ctas = ntiles;
     const size_t need_e = (size_t)ctas * e.O * K * sizeof(float);
@@ -1064,6 +1065,11 @@ extern "C" int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float*
       q.part = (float*)workspace;
       q.N = e.N; q.Hg = e.Hs; q.Wg = e.Ws; q.Cm = e.O; q.Hx = e.Hb; q.Wx = e.Wb; q.Cx = e.I;
       q.k = e.k; q.s = e.s; q.off = -e.p; q.K = K; q.P = (long long)e.N * e.Hs * e.Ws; q.p_per_split = 0;
+      if (ekey == 408) {
+        rc = edge_wgrad_tma(e, q.g, q.x, q.part, (int)ctas, st);
+        if (rc == SGK_OK) return launch_wgrad_reduce((const float*)workspace, dw, e.O, e.I, e.k, (int)ctas, st);
+        if (rc != SGK_EUNSUPPORTED) return rc;
+      }
       dim3 grid((unsigned)ctas, (unsigned)cgroups);
       cudaError_t ce = cudaSuccess;
 #define SGK_EDGE_W(TA_, TBC_)                                                                                           \

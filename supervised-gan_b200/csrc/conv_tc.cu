@@ -395,6 +395,24 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int 
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
+
+// K-major SWIZZLE_32B operand: rows of 32 B (8 tf32 = one MMA's K), 8-row atoms of 256 B
+__device__ __forceinline__ uint64_t make_sw32_kmajor_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO: unused for swizzled K-major
+  d |= (uint64_t)(256 >> 4) << 32;        // SBO: next 8-row group
+  d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+  d |= (uint64_t)6 << 61;                 // SWIZZLE_32B
+  return d;
+}
+
 struct alignas(64) TmaMaps {
   CUtensorMap w[4];  // packed weights per phase
   CUtensorMap a;     // NHWC activations as {C, W, H, N}, box {32, 16*is, 8*is, 1}, traversal strides {1, is, is, 1}
@@ -409,6 +427,11 @@ struct TmaParams {
   GatherPhase ph[4];
   int tiles_x[4], tiles_y[4];
   int BN, stages, tmem_cols;
+  // im2col-by-TMA mode (2-channel image layers, k4 s2, input already zero-padded): the whole K = 4 tap rows x (4 taps x 2 ch)
+  // = 32 floats of an output pixel are 4 contiguous 32-B runs, so ONE 5-D box {8 floats, 16 px, 8 rows, 4 tap rows, 1}
+  // over overlapping strides (pixel stride = s*Cg floats = 16 B) lands the im2col tile in smem as [tap row][pixel][32 B]
+  // (SWIZZLE_32B; the inner box must span the whole swizzle width, a 128-B swizzle with 32-B rows faults): KB = 1.
+  int im2col;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 3)
@@ -436,7 +459,7 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
   const int ty0 = (t / p.tiles_x[phi]) * TT_H, tx0 = (t % p.tiles_x[phi]) * TT_W;
   const int n0 = blockIdx.y * p.BN;
   const int cchunks = p.Cg >> 5;
-  const int KB = P.ta * P.tb * cchunks;
+  const int KB = p.im2col ? 1 : P.ta * P.tb * cchunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -507,7 +530,8 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
         mbar_wait(empty_bar(s), (uint32_t)(((kb / S) & 1) ^ 1));
         mbar_arrive_expect_tx(full_bar(s), tx_bytes);
         const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
-        tma_load_4d(abase, &maps.a, c0, x_base + b, y_base + a, n, full_bar(s));
+        if (p.im2col) tma_load_5d(abase, &maps.a, 0, tx0, ty0, 0, n, full_bar(s));
+        else tma_load_4d(abase, &maps.a, c0, x_base + b, y_base + a, n, full_bar(s));
         tma_load_2d(abase + TC_A_BYTES, wmap, kb * 32, n0, full_bar(s));
         c0 += 32;
         if (c0 >= p.Cg) {
@@ -528,8 +552,8 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
         const uint32_t b_addr = a_addr + TC_A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_tf32(tmem_acc, make_sw128_kmajor_desc(a_addr + kk * 32), make_sw128_kmajor_desc(b_addr + kk * 32), idesc,
-                    (uint32_t)((kb | kk) != 0));
+          umma_tf32(tmem_acc, p.im2col ? make_sw32_kmajor_desc(a_addr + kk * 4096) : make_sw128_kmajor_desc(a_addr + kk * 32),
+                    make_sw128_kmajor_desc(b_addr + kk * 32), idesc, (uint32_t)((kb | kk) != 0));
         umma_commit(empty_bar(s));
       }
       umma_commit(tmem_full_bar);
@@ -858,7 +882,12 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   // Thin-channel problems (Cin < 32 or Cout <= 16) are HBM/issue-bound; measured on B200 the CUDA-core thin kernels
   // beat the tensor-core tile for them (profiles/), so they are only routed here when SGK_TC_THIN=1.
   static const bool tc_thin = getenv("SGK_TC_THIN") != nullptr && atoi(getenv("SGK_TC_THIN")) != 0;
-  if (!tc_thin && ((g.Cg % 32) != 0 || (g.Co % 32) != 0)) return SGK_EUNSUPPORTED;
+  // im2col-by-TMA: direct conv, k4 s2 p0 on a 2-channel (pre-padded) image, full 32-wide N tiles
+  static const bool use_im2col = !(getenv("SGK_TC_IM2COL") != nullptr && atoi(getenv("SGK_TC_IM2COL")) == 0);
+  const bool im2col = use_im2col && g.transposed_type == 0 && g.nphase == 1 && g.k == 4 && g.ph[0].is == 2 && g.ph[0].ioy == 0 &&
+                      g.ph[0].iox == 0 && g.Cg == 2 && (g.Co % 32) == 0 && (g.Wi % 2) == 0 && g.ph[0].kstride == 32 &&
+                      (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  if (!im2col && !tc_thin && ((g.Cg % 32) != 0 || (g.Co % 32) != 0)) return SGK_EUNSUPPORTED;
   // N tile: a divisor of Cout in {256,128,64,32}, or one 16-wide tile for thin outputs (Cout <= 16: images, logits)
   int BN = pick_bn(g.Co);
   if (BN == 0) {
@@ -916,10 +945,11 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   // step); it stays available for experiments with SGK_TC_PERSIST=1.
   // ---- TMA-fed variant: activations as 4-D tensor boxes (needs 32-channel chunks and full 32-column N tiles)
   static const bool use_tma = !(getenv("SGK_TC_TMA") != nullptr && atoi(getenv("SGK_TC_TMA")) == 0);
-  if (use_tma && cs == 0 && BN >= 32) {
+  if (im2col || (use_tma && cs == 0 && BN >= 32)) {
     const int is = g.ph[0].is;
     TmaParams q{};
     TmaMaps tm{};
+    q.im2col = im2col ? 1 : 0;
     q.bias = bias; q.out = out;
     q.N = g.N; q.Cg = g.Cg; q.Ho = g.Ho; q.Wo = g.Wo; q.Co = g.Co;
     q.act = act; q.slope = slope; q.nphase = g.nphase;
@@ -927,6 +957,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
     int tst = 4;
     { const char* ev = getenv("SGK_TMA_STAGES"); if (ev) tst = atoi(ev); }
     while (tst > 2 && (size_t)tst * stage_bytes > 72 * 1024) --tst;   // <= 72 KB of ring per CTA: 3 CTAs per SM
+    if (im2col) tst = 1;                                               // a single k-block per tile: more resident CTAs instead
     q.stages = tst;
     long long mt = 0;
     for (int i = 0; i < g.nphase; ++i) {
@@ -942,8 +973,20 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
     cuuint64_t astr[3] = {(cuuint64_t)g.Cg * 4, (cuuint64_t)g.Wi * g.Cg * 4, (cuuint64_t)g.Hi * g.Wi * g.Cg * 4};
     cuuint32_t abox[4] = {32u, (cuuint32_t)(TT_W * is), (cuuint32_t)(TT_H * is), 1u};
     cuuint32_t aest[4] = {1u, (cuuint32_t)is, (cuuint32_t)is, 1u};
-    CUresult r = encode(&tm.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, adim, astr, abox, aest, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r;
+    if (im2col) {
+      // {8 floats of a tap row, output x, output y, tap row a, image}; x / y strides overlap (s*Cg floats, s rows)
+      const cuuint64_t pitch = (cuuint64_t)g.Wi * g.Cg * 4;
+      cuuint64_t idim[5] = {8u, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, 4u, (cuuint64_t)g.N};
+      cuuint64_t istr[4] = {(cuuint64_t)is * g.Cg * 4, (cuuint64_t)is * pitch, pitch, (cuuint64_t)g.Hi * pitch};
+      cuuint32_t ibox[5] = {8u, (cuuint32_t)TT_W, (cuuint32_t)TT_H, 4u, 1u};
+      cuuint32_t iest[5] = {1u, 1u, 1u, 1u, 1u};
+      r = encode(&tm.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, idim, istr, ibox, iest, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      r = encode(&tm.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, adim, astr, abox, aest, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(activations) failed (%d)", (int)r); return SGK_ECUDA; }
     const size_t tsmem = (size_t)tst * stage_bytes + 8 * (2 * tst + 2) + 1024;
     static bool tattr = false;
@@ -1505,6 +1548,164 @@ static WTcPlan wgrad_tc_plan(const EquivConv& e) {
   }
   w.ok = 1;
   return w;
+}
+
+// ================================================================================================
+// Image-edge weight gradient (2-channel x, k4: K = 32; 32 G channels per CTA column) on the FFMA pipe, fed by TMA:
+// lane = G channel, 32 accumulators (one per (a,b,c)) per thread, one warp per output row of an 8 x 32 pixel tile.  The
+// x patch of a tile ((8-1)*s+4 rows x ((32-1)*s+4)*2 floats) is ONE 3-D tensor box (out-of-range -> zero = padding),
+// double buffered so the next tile's patch is in flight while this one is consumed.  Replaces the division-heavy scalar
+// patch loop of conv_simt.cu's edge_wgrad_kernel (ncu: l1tex 47 %, 23 % warps active) for this shape.
+// ================================================================================================
+constexpr int EW_TH = 8, EW_TW = 32, EW_K = 32;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+               : "memory");
+}
+
+struct EdgeWParams {
+  const float* g;
+  float* part;           // [gridDim.x][Cm][32]
+  int N, Hg, Wg, Cm;
+  int s, off, Cx;
+  int tiles_x, tiles_y;
+  int PH, rowf;          // patch rows, floats per patch row
+  uint32_t buf_stride;   // bytes between the two patch buffers (128-B multiple)
+};
+
+template <int S>   // conv stride: patch geometry is compile-time so that every patch read is base + immediate
+__global__ void __launch_bounds__(256, 3)
+edge_wgrad_tma_kernel(const __grid_constant__ EdgeWParams p, const __grid_constant__ CUtensorMap xmap) {
+  constexpr int ROWF = ((EW_TW - 1) * S + 4) * 2, XSTEP = S * 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 127u) & ~127u;
+  uint8_t* gen = smem_raw + (base - raw_u32);
+  const uint32_t bar0 = base + 2u * p.buf_stride;
+  float* red = reinterpret_cast<float*>(gen + 2u * p.buf_stride + 16u);   // [8 warps][32 lanes][33]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per_img = p.tiles_x * p.tiles_y;
+  const long long ntiles = (long long)per_img * p.N;
+  const int m = blockIdx.y * 32 + lane;
+  const uint32_t patch_bytes = (uint32_t)p.PH * (uint32_t)p.rowf * 4u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8u, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](long long t, int buf) {
+    const int n = (int)(t / per_img);
+    const int r2 = (int)(t - (long long)n * per_img);
+    const int tyi = r2 / p.tiles_x, txi = r2 - tyi * p.tiles_x;
+    mbar_arrive_expect_tx(bar0 + 8u * (uint32_t)buf, patch_bytes);
+    tma_load_3d(base + (uint32_t)buf * p.buf_stride, &xmap, (txi * EW_TW * p.s + p.off) * p.Cx, tyi * EW_TH * p.s + p.off, n,
+                bar0 + 8u * (uint32_t)buf);
+  };
+  float acc[EW_K];
+#pragma unroll
+  for (int k = 0; k < EW_K; ++k) acc[k] = 0.f;
+  if (threadIdx.x == 0 && (long long)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    // the other buffer was consumed in the previous iteration (trailing __syncthreads): refill it now
+    if (threadIdx.x == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x, buf ^ 1);
+    const int n = (int)(t / per_img);
+    const int r2 = (int)(t - (long long)n * per_img);
+    const int tyi = r2 / p.tiles_x, txi = r2 - tyi * p.tiles_x;
+    const int oy = tyi * EW_TH + warp, ox0 = txi * EW_TW;
+    // G values of this warp's row segment first: they do not depend on the patch
+    float gq[EW_TW];
+    if (oy < p.Hg) {
+      const float* __restrict__ grow = p.g + (((long long)n * p.Hg + oy) * p.Wg) * p.Cm + m;
+#pragma unroll
+      for (int xl = 0; xl < EW_TW; ++xl) gq[xl] = (m < p.Cm && ox0 + xl < p.Wg) ? __ldg(grow + (long long)(ox0 + xl) * p.Cm) : 0.f;
+    }
+    mbar_wait(bar0 + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));
+    if (oy < p.Hg) {
+      const float* patch = reinterpret_cast<const float*>(gen + (uint32_t)buf * p.buf_stride);
+      const float* prow = patch + (warp * S) * ROWF;
+#pragma unroll
+      for (int xl = 0; xl < EW_TW; ++xl) {
+        const float gv = gq[xl];
+        const float* pp0 = prow + xl * XSTEP;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int r = 0; r < 8; r += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(pp0 + a * ROWF + r);
+            acc[a * 8 + r + 0] = fmaf(gv, v.x, acc[a * 8 + r + 0]);
+            acc[a * 8 + r + 1] = fmaf(gv, v.y, acc[a * 8 + r + 1]);
+            acc[a * 8 + r + 2] = fmaf(gv, v.z, acc[a * 8 + r + 2]);
+            acc[a * 8 + r + 3] = fmaf(gv, v.w, acc[a * 8 + r + 3]);
+          }
+      }
+    }
+    __syncthreads();   // patch[buf] fully consumed
+  }
+  // fixed-order reduction over the 8 warps (rows padded to 33 floats: conflict-free), one partial block per CTA
+#pragma unroll
+  for (int k = 0; k < EW_K; ++k) red[((size_t)warp * 32 + lane) * 33 + k] = acc[k];
+  __syncthreads();
+  {
+    // 256 threads: thread -> (channel lane, 4 of the 32 k's)
+    const int cl = threadIdx.x & 31, kq = threadIdx.x >> 5;
+    const int mm = blockIdx.y * 32 + cl;
+    if (mm < p.Cm) {
+      float* dst = p.part + ((long long)blockIdx.x * p.Cm + mm) * EW_K;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = kq * 4 + kk;
+        float sacc = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) sacc += red[((size_t)wq * 32 + cl) * 33 + k];
+        dst[k] = sacc;
+      }
+    }
+  }
+}
+
+// returns SGK_EUNSUPPORTED when the shape / alignment does not fit (the caller keeps its own kernel)
+int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* part, int ctas, cudaStream_t st) {
+  static const bool on = !(getenv("SGK_EDGE_TMA") != nullptr && atoi(getenv("SGK_EDGE_TMA")) == 0);
+  if (!on || e.k != 4 || e.I != 2 || e.s > 2) return SGK_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || ((long long)e.Wb * e.I * 4) % 16 != 0 || (e.p * e.I * 4) % 16 != 0 ||
+      (EW_TW * e.s * e.I * 4) % 16 != 0)
+    return SGK_EUNSUPPORTED;
+  EncodeTiledFn encode = get_encode_tiled();
+  if (!encode) return SGK_EUNSUPPORTED;
+  EdgeWParams q{};
+  q.g = g; q.part = part;
+  q.N = e.N; q.Hg = e.Hs; q.Wg = e.Ws; q.Cm = e.O; q.s = e.s; q.off = -e.p; q.Cx = e.I;
+  q.tiles_x = ceil_div(e.Ws, EW_TW); q.tiles_y = ceil_div(e.Hs, EW_TH);
+  q.PH = (EW_TH - 1) * e.s + e.k;
+  q.rowf = ((EW_TW - 1) * e.s + e.k) * e.I;
+  if (q.rowf > 256 || (q.rowf * 4) % 16 != 0) return SGK_EUNSUPPORTED;
+  q.buf_stride = ((uint32_t)q.PH * q.rowf * 4u + 127u) & ~127u;
+  CUtensorMap xmap;
+  cuuint64_t dim[3] = {(cuuint64_t)e.Wb * e.I, (cuuint64_t)e.Hb, (cuuint64_t)e.N};
+  cuuint64_t str[2] = {(cuuint64_t)e.Wb * e.I * 4, (cuuint64_t)e.Hb * e.Wb * e.I * 4};
+  cuuint32_t box[3] = {(cuuint32_t)q.rowf, (cuuint32_t)q.PH, 1u};
+  cuuint32_t es[3] = {1u, 1u, 1u};
+  CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return SGK_EUNSUPPORTED;
+  const size_t smem = 2 * (size_t)q.buf_stride + 16 + (size_t)8 * 32 * 33 * sizeof(float) + 128;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t ce = cudaFuncSetAttribute(edge_wgrad_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(edge_wgrad_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(edge_wgrad_tma_kernel)");
+    attr = true;
+  }
+  dim3 grid((unsigned)ctas, (unsigned)ceil_div(e.O, 32));
+  if (e.s == 1) edge_wgrad_tma_kernel<1><<<grid, 256, smem, st>>>(q, xmap);
+  else edge_wgrad_tma_kernel<2><<<grid, 256, smem, st>>>(q, xmap);
+  SGK_LAUNCH_CHECK("edge_wgrad_tma_kernel");
+  return SGK_OK;
 }
 
 size_t conv_wgrad_tc_workspace_bytes(const SgkConvDesc* d) {

@@ -82,6 +82,33 @@ __global__ void tap_unfold_kernel(const float* __restrict__ dy, float* __restric
   }
 }
 
+// zero-padded copy of an NHWC tensor (the im2col-by-TMA path of conv_tc.cu reads image layers from a padded buffer so that
+// every patch is in bounds); one thread per output pixel channel-vector
+template <int V>
+__global__ void pad_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int pad) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int cv = C / V;
+  const long long total = (long long)N * Hp * Wp * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long pix = i / cv;
+    const int px = (int)(pix % Wp);
+    pix /= Wp;
+    const int py = (int)(pix % Hp);
+    const int n = (int)(pix / Hp);
+    const int iy = py - pad, ix = px - pad;
+    const bool in = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+    const long long src = ((((long long)n * H + iy) * W + ix) * cv + c);
+    if (V == 4) {
+      reinterpret_cast<float4*>(y)[i] = in ? __ldg(reinterpret_cast<const float4*>(x) + src) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (V == 2) {
+      reinterpret_cast<float2*>(y)[i] = in ? __ldg(reinterpret_cast<const float2*>(x) + src) : make_float2(0.f, 0.f);
+    } else {
+      y[i] = in ? __ldg(x + src) : 0.f;
+    }
+  }
+}
+
 static inline unsigned tap_blocks(long long n) {
   long long b = (n + 255) / 256;
   const long long cap = 148LL * 16;
@@ -138,5 +165,18 @@ extern "C" int sgk_tap_unfold(const float* dy, float* g32, int N, int H, int W, 
   tap_unfold_kernel<<<tap_blocks((long long)N * H * W * TAP_ROWS), 256, 0, (cudaStream_t)stream>>>(dy, g32, N, H, W, Ho, Wo, Cout, k,
                                                                                                   pad);
   SGK_LAUNCH_CHECK("tap_unfold_kernel");
+  return SGK_OK;
+}
+
+extern "C" int sgk_pad_nhwc(const float* x, float* y, int N, int H, int W, int C, int pad, void* stream) {
+  SGK_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0, "sgk_pad_nhwc: bad argument");
+  const long long pix = (long long)N * (H + 2 * pad) * (W + 2 * pad);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool a16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  const bool a8 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 7) == 0;
+  if (C % 4 == 0 && a16) pad_nhwc_kernel<4><<<tap_blocks(pix * (C / 4)), 256, 0, st>>>(x, y, N, H, W, C, pad);
+  else if (C % 2 == 0 && a8) pad_nhwc_kernel<2><<<tap_blocks(pix * (C / 2)), 256, 0, st>>>(x, y, N, H, W, C, pad);
+  else pad_nhwc_kernel<1><<<tap_blocks(pix * C), 256, 0, st>>>(x, y, N, H, W, C, pad);
+  SGK_LAUNCH_CHECK("pad_nhwc_kernel");
   return SGK_OK;
 }

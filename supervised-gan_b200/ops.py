@@ -14,6 +14,7 @@ from . import _lib as L
 
 _precision = L.FP32
 _weights_epoch = 0
+_im2col = os.environ.get("SGK_IM2COL", "1") != "0"       # padded-copy + im2col-by-TMA for 2-channel image layers
 _tap_fold = os.environ.get("SGK_TAP_FOLD", "1") != "0"   # tap-folded thin heads on the tensor-core paths (csrc/taps.cu)
 
 
@@ -151,6 +152,14 @@ class ConvCfg:
         self._packed[op] = (tag, buf)
         return buf
 
+    # ---- image layers (2-channel input, k4 s2) on the tensor-core path: convolve a zero-padded copy with pad=0 so that one
+    # TMA box fetches a whole im2col tile (conv_tc.cu "im2col" mode)
+    def padded_image_layer(self, weight, x_shape):
+        if self.transposed or self.stride != 2 or self.k != 4 or self.pad <= 0 or _precision == L.FP32 or not _im2col:
+            return False
+        cout, cin = weight.shape[0], weight.shape[1]
+        return cin == 2 and cout % 32 == 0 and x_shape[2] % 2 == 0
+
     # ---- tap-folded evaluation of thin-output stride-1 convs (csrc/taps.cu): Cout*k*k <= 32 rows of a 1x1 conv
     def tap_folded(self, weight, x_shape):
         if self.transposed or self.stride != 1 or self.k == 1 or _precision == L.FP32 or not _tap_fold:
@@ -191,6 +200,7 @@ class _ConvFn(torch.autograd.Function):
         desc = cfg.desc(x.shape, w)
         y = torch.empty((desc.N, desc.Hout, desc.Wout, desc.Cout), dtype=torch.float32, device=x.device)
         ctx.tap = cfg.tap_folded(w, x.shape)
+        ctx.descp = None
         if ctx.tap:
             st = _stream()
             desc1, _, wp1, _ = cfg.tap_weights(w, x.shape)
@@ -199,10 +209,23 @@ class _ConvFn(torch.autograd.Function):
                 ctypes.byref(desc1), _p(x), _p(wp1), None, _p(t), L.ACT_NONE, 0.0, st)), "conv_fwd(tap 1x1)")
             L.check(lib.sgk_tap_fold_fwd(_p(t), _p(b), _p(y), desc.N, desc.Hin, desc.Win, desc.Cout, desc.k, desc.pad, act,
                                          slope, st), "tap_fold_fwd")
+        elif cfg.padded_image_layer(w, x.shape):
+            st = _stream()
+            pd = desc.pad
+            xp = torch.empty((desc.N, desc.Hin + 2 * pd, desc.Win + 2 * pd, desc.Cin), dtype=torch.float32, device=x.device)
+            L.check(lib.sgk_pad_nhwc(_p(x), _p(xp), desc.N, desc.Hin, desc.Win, desc.Cin, pd, st), "pad_nhwc")
+            descp = L.SgkConvDesc(desc.N, desc.Cin, desc.Hin + 2 * pd, desc.Win + 2 * pd, desc.Cout, desc.Hout, desc.Wout,
+                                  desc.k, desc.stride, 0, 0, desc.precision)
+            wp = cfg.packed(weight, desc, L.OP_FWD)      # the packed layout does not depend on the padding
+            L.check(_timed(_conv_tag("fwd", descp), _conv_flops(descp), lambda: lib.sgk_conv_fwd(
+                ctypes.byref(descp), _p(xp), _p(wp), _p(b), _p(y), act, slope, st)), "conv_fwd(padded)")
+            ctx.descp = descp
+            x = xp                                        # the weight gradient is taken from the padded copy as well
         else:
             wp = cfg.packed(weight, desc, L.OP_FWD)
             L.check(_timed(_conv_tag("fwd", desc), _conv_flops(desc), lambda: lib.sgk_conv_fwd(
                 ctypes.byref(desc), _p(x), _p(wp), _p(b), _p(y), act, slope, _stream())), "conv_fwd")
+        ctx.x_shape = (desc.N, desc.Hin, desc.Win, desc.Cin)
         ctx.cfg, ctx.desc, ctx.has_bias = cfg, desc, bias is not None
         # a conv bias that feeds an Instance/BatchNorm has an exactly-zero gradient (the norm removes the mean);
         # we emit exact zeros instead of the reference's ~1e-9 rounding noise (DESIGN.md "deviations")
@@ -249,7 +272,7 @@ class _ConvFn(torch.autograd.Function):
                     L.check(lib.sgk_bias_grad(_p(dy), _p(gb), rows, desc.Cout, _p(ws), ws.numel(), st), "bias_grad")
             return gx, gw, gb, None, None, None, None
         if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
+            gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dy.device)
             wp = cfg.packed(weight, desc, L.OP_DGRAD)
             L.check(_timed(_conv_tag("dgrad", desc), _conv_flops(desc), lambda: lib.sgk_conv_dgrad(
                 ctypes.byref(desc), _p(dy), _p(wp), _p(gx), st)), "conv_dgrad")
@@ -261,10 +284,11 @@ class _ConvFn(torch.autograd.Function):
             gw = torch.empty_like(weight)
             if want_b:
                 gb = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device)
-            nbytes = lib.sgk_conv_wgrad_workspace_bytes(ctypes.byref(desc))
+            wdesc = ctx.descp if ctx.descp is not None else desc
+            nbytes = lib.sgk_conv_wgrad_workspace_bytes(ctypes.byref(wdesc))
             ws = _ws(nbytes, dy.device)
-            L.check(_timed(_conv_tag("wgrad", desc), _conv_flops(desc), lambda: lib.sgk_conv_wgrad(
-                ctypes.byref(desc), _p(x), _p(dy), _p(gw), _p(gb) if want_b else None, _p(ws), ws.numel(), st)), "conv_wgrad")
+            L.check(_timed(_conv_tag("wgrad", wdesc), _conv_flops(wdesc), lambda: lib.sgk_conv_wgrad(
+                ctypes.byref(wdesc), _p(x), _p(dy), _p(gw), _p(gb) if want_b else None, _p(ws), ws.numel(), st)), "conv_wgrad")
         elif want_b:
             gb = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device)
             rows = dy.numel() // desc.Cout

@@ -51,6 +51,8 @@ TC_CASES = [  # transposed, N, Cin, Cout, H, W, k, s, p  (all channel counts mul
     (0, 2, 3, 64, 20, 20, 4, 2, 2), (1, 2, 8, 256, 8, 8, 4, 2, 1), (0, 1, 10, 64, 8, 8, 3, 1, 1),
     (0, 1, 2, 64, 16, 16, 3, 1, 1), (0, 1, 64, 1, 16, 16, 3, 1, 1), (1, 1, 128, 1, 8, 8, 4, 2, 1), (0, 1, 1, 32, 32, 32, 4, 2, 1),
     # tap-folded heads (Cout*k*k <= 32, stride 1): 1x1 conv + fold (csrc/taps.cu)
+    # image layers: padded copy + im2col-by-TMA (2-channel input, k4 s2, even width)
+    (0, 3, 2, 64, 64, 64, 4, 2, 2), (0, 2, 2, 32, 34, 130, 4, 2, 1),
     (0, 2, 256, 2, 19, 17, 4, 1, 2), (0, 3, 256, 1, 66, 66, 4, 1, 2), (0, 1, 32, 3, 9, 12, 3, 1, 0),
 ]
 
