@@ -432,6 +432,8 @@ struct TmaParams {
   // over overlapping strides (pixel stride = s*Cg floats = 16 B) lands the im2col tile in smem as [tap row][pixel][32 B]
   // (SWIZZLE_32B; the inner box must span the whole swizzle width, a 128-B swizzle with 32-B rows faults): KB = 1.
   int im2col;
+  // output-pixel tile of a CTA: tw x th <= 128 pixels, chosen per layer to minimise ragged-edge waste (66 x 66 -> 11 x 11)
+  int tw, th;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 3)
@@ -456,7 +458,7 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
   const int per_img = p.tiles_x[phi] * p.tiles_y[phi];
   const int n = t / per_img;
   t -= n * per_img;
-  const int ty0 = (t / p.tiles_x[phi]) * TT_H, tx0 = (t % p.tiles_x[phi]) * TT_W;
+  const int ty0 = (t / p.tiles_x[phi]) * p.th, tx0 = (t % p.tiles_x[phi]) * p.tw;
   const int n0 = blockIdx.y * p.BN;
   const int cchunks = p.Cg >> 5;
   const int KB = p.im2col ? 1 : P.ta * P.tb * cchunks;
@@ -506,12 +508,13 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = warp * 32 + i * 4 + rsub;
-        const int oy = ty0 + r / TT_W, ox = tx0 + r % TT_W;
+        const int ry = r / p.tw;
+        const int oy = ty0 + ry, ox = tx0 + (r - ry * p.tw);
         float4 o;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
                      : "r"(stg + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
-        if (oy < P.Hp && ox < P.Wp) {
+        if (ry < p.th && oy < P.Hp && ox < P.Wp) {
           float* dstp = p.out + (((long long)n * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co + n0 + cc + 4 * j;
           *reinterpret_cast<float4*>(dstp) = o;
         }
@@ -522,7 +525,7 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
     // =============================================================== TMA producer (activations + weights)
     if (lane == 0) {
       const void* wmap = &maps.w[phi];
-      const uint32_t tx_bytes = (uint32_t)TC_A_BYTES + (uint32_t)p.BN * 128u;
+      const uint32_t tx_bytes = (uint32_t)(p.tw * p.th) * 128u + (uint32_t)p.BN * 128u;
       const int x_base = tx0 * P.is + P.iox, y_base = ty0 * P.is + P.ioy;
       int a = 0, b = 0, c0 = 0;
       for (int kb = 0; kb < KB; ++kb) {
@@ -959,19 +962,36 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
     while (tst > 2 && (size_t)tst * stage_bytes > 72 * 1024) --tst;   // <= 72 KB of ring per CTA: 3 CTAs per SM
     if (im2col) tst = 1;                                               // a single k-block per tile: more resident CTAs instead
     q.stages = tst;
+    // tile shape: the (tw, th), tw*th <= 128, with the fewest tiles over all phases (ties: the squarer one, whose halo
+    // overlap between taps is largest); the im2col slab layout needs the fixed 16 x 8
+    q.tw = TT_W; q.th = TT_H;
+    static const bool flex = !(getenv("SGK_TC_FLEXTILE") != nullptr && atoi(getenv("SGK_TC_FLEXTILE")) == 0);
+    if (!im2col && flex) {
+      long long best = -1;
+      int bw = TT_W, bh = TT_H;
+      for (int w = 1; w <= 128; ++w) {
+        const int h = 128 / w;
+        if (w * is > 256 || h * is > 256) continue;
+        long long cnt = 0;
+        for (int i = 0; i < g.nphase; ++i) cnt += (long long)ceil_div(g.ph[i].Wp, w) * ceil_div(g.ph[i].Hp, h);
+        const int sq = w > h ? w - h : h - w, bsq = bw > bh ? bw - bh : bh - bw;
+        if (best < 0 || cnt < best || (cnt == best && sq < bsq)) { best = cnt; bw = w; bh = h; }
+      }
+      q.tw = bw; q.th = bh;
+    }
     long long mt = 0;
     for (int i = 0; i < g.nphase; ++i) {
       q.ph[i] = g.ph[i];
       q.ph[i].m_tile_begin = (int)mt;
-      q.tiles_x[i] = ceil_div(g.ph[i].Wp, TT_W);
-      q.tiles_y[i] = ceil_div(g.ph[i].Hp, TT_H);
+      q.tiles_x[i] = ceil_div(g.ph[i].Wp, q.tw);
+      q.tiles_y[i] = ceil_div(g.ph[i].Hp, q.th);
       mt += (long long)g.N * q.tiles_x[i] * q.tiles_y[i];
       tm.w[i] = maps.w[i];
     }
     if (mt > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return SGK_EUNSUPPORTED; }
     cuuint64_t adim[4] = {(cuuint64_t)g.Cg, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
     cuuint64_t astr[3] = {(cuuint64_t)g.Cg * 4, (cuuint64_t)g.Wi * g.Cg * 4, (cuuint64_t)g.Hi * g.Wi * g.Cg * 4};
-    cuuint32_t abox[4] = {32u, (cuuint32_t)(TT_W * is), (cuuint32_t)(TT_H * is), 1u};
+    cuuint32_t abox[4] = {32u, (cuuint32_t)(q.tw * is), (cuuint32_t)(q.th * is), 1u};
     cuuint32_t aest[4] = {1u, (cuuint32_t)is, (cuuint32_t)is, 1u};
     CUresult r;
     if (im2col) {
@@ -1538,7 +1558,11 @@ static WTcPlan wgrad_tc_plan(const EquivConv& e) {
     w.tiles_x = ceil_div(e.Ws, WT_W);
     w.tiles_y = ceil_div(e.Hs, WT_H);
     w.T = (long long)e.N * w.tiles_x * w.tiles_y;
-    long long sp = ceil_div64(2LL * 3 * sm_count(), tiles);
+    // pixel splits: enough CTAs for `waves` x 2 resident CTAs per SM; every split costs one O x K partial block of
+    // HBM traffic (written here, re-read by the reduce), so fewer, longer CTAs win once the machine is full
+    // (rounded DOWN: one CTA more than the resident slots would run a second, nearly empty wave)
+    static const int waves = getenv("SGK_WTMA_WAVES") ? atoi(getenv("SGK_WTMA_WAVES")) : 1;
+    long long sp = (2LL * (waves < 1 ? 1 : waves) * sm_count()) / tiles;
     long long maxsp = ceil_div64(w.T, 8);
     if (sp > maxsp) sp = maxsp;
     if (sp < 1) sp = 1;

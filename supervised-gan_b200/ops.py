@@ -28,11 +28,26 @@ def get_precision():
     return {v: k for k, v in L.PRECISION.items()}[_precision]
 
 
-def bump_weights_epoch():
-    """Invalidate every packed-weight cache (called by the fused optimiser, load_state_dict, weights_init
-    and graph replays -- anything that changes parameter memory behind autograd's back)."""
-    global _weights_epoch
-    _weights_epoch += 1
+_param_epoch = {}     # data_ptr -> epoch of the last out-of-band update of that parameter
+_epoch_counter = 0
+
+
+def bump_weights_epoch(params=None):
+    """Invalidate packed-weight caches after parameter memory changed behind autograd's back (fused optimiser,
+    load_state_dict, weights_init, graph replays).  With `params` only those tensors' caches are invalidated -- Adam(D) must
+    not force the generator's weights to be re-packed and vice versa; without, every cache."""
+    global _weights_epoch, _epoch_counter
+    if params is None:
+        _weights_epoch += 1
+        return
+    _epoch_counter += 1
+    for p in params:
+        _param_epoch[p.data_ptr()] = _epoch_counter
+
+
+def _weight_tag(weight):
+    ptr = weight.data_ptr()
+    return (weight._version, _weights_epoch, _param_epoch.get(ptr, 0), ptr, _precision)
 
 
 def _stream():
@@ -141,7 +156,7 @@ class ConvCfg:
 
     def packed(self, weight, desc, op):
         lib = L.load()
-        tag = (weight._version, _weights_epoch, weight.data_ptr(), _precision)
+        tag = _weight_tag(weight)
         ent = self._packed.get(op)
         if ent is not None and ent[0] == tag:
             return ent[1]
@@ -173,7 +188,7 @@ class ConvCfg:
         N, H, W, C = x_shape
         cout, cin = weight.shape[0], weight.shape[1]
         desc1 = L.SgkConvDesc(N, cin, H, W, 32, H, W, 1, 1, 0, 0, _precision)
-        tag = (weight._version, _weights_epoch, weight.data_ptr(), _precision)
+        tag = _weight_tag(weight)
         ent = self._packed.get("tap")
         if ent is None or ent[0] != tag:
             st = _stream()

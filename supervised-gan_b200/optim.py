@@ -71,7 +71,7 @@ class FusedAdam(torch.optim.Optimizer):
                 arr[i].p, arr[i].g, arr[i].m, arr[i].v, arr[i].n = e
             L.check(lib.sgk_adam_multi_tensor(arr, len(entries), st["step"].data_ptr(), st["hyper"].data_ptr(), stream),
                     "adam_multi_tensor")
-        ops.bump_weights_epoch()
+        ops.bump_weights_epoch([p for group in self.param_groups for p in group["params"]])
         return None
 
     def step_count(self, gi=0):
