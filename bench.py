@@ -107,6 +107,10 @@ def cpu_oracle_throughput(batch, steps, warmup, seed=0):
     return batch * steps / dt, dt / steps, torch.get_num_threads()
 
 
+WORKLOAD = ("fcgan 512x512 G+D step (BASELINE configs[3]): deconv G n_layers 5 ngf 32 noise 8x8x8 + "
+            "3-scale n_layers D ndf 32 scale 1/2/4, instance norm, BCE, 2 channels, pool_size 0")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -119,7 +123,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "fcgan 512x512 G+D step, deconv G ngf32 + 3-scale D ndf32, BCE, batch %d (CPU sample)" % b},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "cpu_sample_batch": b},
             "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -315,8 +319,7 @@ def run_ours(args):
                 "ms_per_step": ms / args.steps, "steps_per_sec": args.steps / (ms * 1e-3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
-                "config": {"workload": "fcgan 512x512 G+D step (BASELINE configs[3]): deconv G n_layers 5 ngf 32 noise 8x8x8 + "
-                                       "3-scale n_layers D ndf 32 scale 1/2/4, instance norm, BCE, 2 channels, pool_size 0",
+                "config": {"workload": WORKLOAD,
                            "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                            "cuda_graph": used_graph,
                            "l2": "inputs larger than L2: the step streams > 1 GB of activations per replay (126 MB L2), no flush"},

@@ -21,116 +21,9 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include "tc_ptx.cuh"
+
 namespace sgk {
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// 4- and 8-byte variants (thin-channel gathers); .ca is the only cache operator allowed below 16 bytes
-__device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
-//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024)   [46,48) version = 1   [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format TF32 (2) @7/@10,
-// a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24
-__host__ __device__ inline uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------------------------ kernel
 struct alignas(64) TcMaps {
@@ -434,15 +327,20 @@ struct TmaParams {
   int im2col;
   // output-pixel tile of a CTA: tw x th <= 128 pixels, chosen per layer to minimise ragged-edge waste (66 x 66 -> 11 x 11)
   int tw, th;
+  // M tiles per CTA: with 2, two accumulators (2*BN TMEM columns) share every weight k-block, which cuts the L2 -> smem
+  // traffic per FLOP of wide-N layers by up to 1.5x (they are L2-bandwidth bound)
+  int mt;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 3)
+__global__ void __launch_bounds__(TC_THREADS, 4)
 conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ TmaMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
-  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.BN * 128u;
+  const int MT = p.mt;                                     // M tiles per CTA (1 or 2) sharing every weight k-block
+  const uint32_t b_off = (uint32_t)MT * TC_A_BYTES;       // stage = MT activation tiles, then the weight tile
+  const uint32_t stage_bytes = b_off + (uint32_t)p.BN * 128u;
   const uint32_t bar_base = smem_base + (uint32_t)S * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
@@ -454,24 +352,53 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
   for (int i = 1; i < 4; ++i)
     if (i < p.nphase && (int)blockIdx.x >= p.ph[i].m_tile_begin) phi = i;
   const GatherPhase P = p.ph[phi];
-  int t = (int)blockIdx.x - P.m_tile_begin;
   const int per_img = p.tiles_x[phi] * p.tiles_y[phi];
-  const int n = t / per_img;
-  t -= n * per_img;
-  const int ty0 = (t / p.tiles_x[phi]) * p.th, tx0 = (t % p.tiles_x[phi]) * p.tw;
+  const int phase_tiles = per_img * p.N;
+  const int t_first = ((int)blockIdx.x - P.m_tile_begin) * MT;
+  const int nvalid = (MT == 2 && t_first + 1 < phase_tiles) ? 2 : 1;
+  int tn[2], tyv[2], txv[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    int t = t_first + (q < nvalid ? q : 0);
+    tn[q] = t / per_img;
+    t -= tn[q] * per_img;
+    tyv[q] = (t / p.tiles_x[phi]) * p.th;
+    txv[q] = (t % p.tiles_x[phi]) * p.tw;
+  }
   const int n0 = blockIdx.y * p.BN;
   const int cchunks = p.Cg >> 5;
   const int KB = p.im2col ? 1 : P.ta * P.tb * cchunks;
 
-  if (threadIdx.x == 0) {
+  // The TMA lane initialises the barriers itself and puts the first min(S, KB) stages in flight BEFORE the CTA-wide
+  // sync, so the load latency of short tiles (1-8 k-blocks) overlaps the TMEM allocation and the barrier handshake.
+  const uint32_t tx_bytes = (uint32_t)nvalid * (uint32_t)(p.tw * p.th) * 128u + (uint32_t)p.BN * 128u;
+  int pa = 0, pb = 0, pc0 = 0, kb_issued = 0;
+  auto issue_kb = [&](int kb) {
+    const int s = kb % S;
+    mbar_arrive_expect_tx(full_bar(s), tx_bytes);
+    const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
+    for (int q = 0; q < nvalid; ++q) {
+      if (p.im2col) tma_load_5d(abase + q * TC_A_BYTES, &maps.a, 0, txv[q], tyv[q], 0, tn[q], full_bar(s));
+      else tma_load_4d(abase + q * TC_A_BYTES, &maps.a, pc0, txv[q] * P.is + P.iox + pb, tyv[q] * P.is + P.ioy + pa, tn[q], full_bar(s));
+    }
+    tma_load_2d(abase + b_off, &maps.w[phi], kb * 32, n0, full_bar(s));
+    pc0 += 32;
+    if (pc0 >= p.Cg) {
+      pc0 = 0;
+      if (++pb == P.tb) { pb = 0; ++pa; }
+    }
+  };
+  if (warp == 4 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);   // one arrive.expect_tx by the TMA thread (both boxes complete_tx on it)
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
+    const int first = KB < S ? KB : S;
+    for (; kb_issued < first; ++kb_issued) issue_kb(kb_issued);
   }
-  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -487,9 +414,12 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
     const int r_own = warp * 32 + lane;
     const uint32_t stg = smem_base;   // stage 0's A region is idle once the accumulator is complete
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
-    for (int cc = 0; cc < p.BN; cc += 32) {
+    for (int qc = 0; qc < nvalid * p.BN; qc += 32) {
+      const int q = qc >= p.BN ? 1 : 0;
+      const int cc = qc - q * p.BN;
+      const int ty0 = tyv[q], tx0 = txv[q], n = tn[q];
       uint32_t v[32];
-      tmem_ld32(lane_addr + (uint32_t)cc, v);
+      tmem_ld32(lane_addr + (uint32_t)qc, v);
       tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -524,23 +454,9 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
   } else if (warp == 4) {
     // =============================================================== TMA producer (activations + weights)
     if (lane == 0) {
-      const void* wmap = &maps.w[phi];
-      const uint32_t tx_bytes = (uint32_t)(p.tw * p.th) * 128u + (uint32_t)p.BN * 128u;
-      const int x_base = tx0 * P.is + P.iox, y_base = ty0 * P.is + P.ioy;
-      int a = 0, b = 0, c0 = 0;
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % S;
-        mbar_wait(empty_bar(s), (uint32_t)(((kb / S) & 1) ^ 1));
-        mbar_arrive_expect_tx(full_bar(s), tx_bytes);
-        const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
-        if (p.im2col) tma_load_5d(abase, &maps.a, 0, tx0, ty0, 0, n, full_bar(s));
-        else tma_load_4d(abase, &maps.a, c0, x_base + b, y_base + a, n, full_bar(s));
-        tma_load_2d(abase + TC_A_BYTES, wmap, kb * 32, n0, full_bar(s));
-        c0 += 32;
-        if (c0 >= p.Cg) {
-          c0 = 0;
-          if (++b == P.tb) { b = 0; ++a; }
-        }
+      for (int kb = kb_issued; kb < KB; ++kb) {
+        mbar_wait(empty_bar(kb % S), (uint32_t)(((kb / S) & 1) ^ 1));
+        issue_kb(kb);
       }
     }
   } else {
@@ -552,11 +468,14 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
         mbar_wait(full_bar(s), (uint32_t)((kb / S) & 1));
         tc_fence_after();
         const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-        const uint32_t b_addr = a_addr + TC_A_BYTES;
+        const uint32_t b_addr = a_addr + b_off;
+        for (int q = 0; q < nvalid; ++q) {
+          const uint32_t aq = a_addr + (uint32_t)q * TC_A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_tf32(tmem_acc, p.im2col ? make_sw32_kmajor_desc(a_addr + kk * 4096) : make_sw128_kmajor_desc(a_addr + kk * 32),
-                    make_sw128_kmajor_desc(b_addr + kk * 32), idesc, (uint32_t)((kb | kk) != 0));
+          for (int kk = 0; kk < 4; ++kk)
+            umma_tf32(tmem_acc + (uint32_t)(q * p.BN), p.im2col ? make_sw32_kmajor_desc(aq + kk * 4096) : make_sw128_kmajor_desc(aq + kk * 32),
+                      make_sw128_kmajor_desc(b_addr + kk * 32), idesc, (uint32_t)((kb | kk) != 0));
+        }
         umma_commit(empty_bar(s));
       }
       umma_commit(tmem_full_bar);
@@ -564,7 +483,7 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+  if (warp == 5) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
 }
 
 // ================================================================================================
@@ -956,12 +875,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
     q.bias = bias; q.out = out;
     q.N = g.N; q.Cg = g.Cg; q.Ho = g.Ho; q.Wo = g.Wo; q.Co = g.Co;
     q.act = act; q.slope = slope; q.nphase = g.nphase;
-    q.BN = BN; q.tmem_cols = BN < 32 ? 32 : BN;
-    int tst = 4;
-    { const char* ev = getenv("SGK_TMA_STAGES"); if (ev) tst = atoi(ev); }
-    while (tst > 2 && (size_t)tst * stage_bytes > 72 * 1024) --tst;   // <= 72 KB of ring per CTA: 3 CTAs per SM
-    if (im2col) tst = 1;                                               // a single k-block per tile: more resident CTAs instead
-    q.stages = tst;
+    q.BN = BN;
     // tile shape: the (tw, th), tw*th <= 128, with the fewest tiles over all phases (ties: the squarer one, whose halo
     // overlap between taps is largest); the im2col slab layout needs the fixed 16 x 8
     q.tw = TT_W; q.th = TT_H;
@@ -979,13 +893,36 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
       }
       q.tw = bw; q.th = bh;
     }
+    long long all_tiles = 0;
+    for (int i = 0; i < g.nphase; ++i) {
+      q.tiles_x[i] = ceil_div(g.ph[i].Wp, q.tw);
+      q.tiles_y[i] = ceil_div(g.ph[i].Hp, q.th);
+      all_tiles += (long long)g.N * q.tiles_x[i] * q.tiles_y[i];
+    }
+    // two M tiles per CTA for wide-N layers once there are enough tiles to fill the machine twice over
+    static const int mt_env = getenv("SGK_TC_MT") ? atoi(getenv("SGK_TC_MT")) : 0;
+    q.mt = 1;
+    // (BN = 256 would need all 512 TMEM columns -> one CTA per SM with an exposed epilogue: measured slower)
+    static const int mt_minbn = getenv("SGK_TC_MT_MINBN") ? atoi(getenv("SGK_TC_MT_MINBN")) : 32;
+    if (!im2col && 2 * BN <= 512 &&
+        (mt_env == 2 || (mt_env == 0 && BN >= mt_minbn && BN <= 128 && all_tiles * (g.Co / BN) >= 2LL * sm_count())))
+      q.mt = 2;
+    const int tcols = q.mt * BN;
+    q.tmem_cols = tcols <= 32 ? 32 : (tcols <= 64 ? 64 : (tcols <= 128 ? 128 : (tcols <= 256 ? 256 : 512)));
+    const uint32_t tstage_bytes = (uint32_t)q.mt * TC_A_BYTES + (uint32_t)BN * 128u;
+    int tst = 4;
+    { const char* ev = getenv("SGK_TMA_STAGES"); if (ev) tst = atoi(ev); }
+    // ring budget: <= 72 KB per CTA (3 CTAs per SM) -- or, when the accumulators take the whole tensor memory (one CTA per
+    // SM anyway), up to 200 KB
+    const size_t ring_budget = q.tmem_cols == 512 ? 200 * 1024 : (q.tmem_cols == 256 ? 100 * 1024 : 72 * 1024);
+    while (tst > 2 && (size_t)tst * tstage_bytes > ring_budget) --tst;
+    if (im2col) tst = 1;                                               // a single k-block per tile: more resident CTAs instead
+    q.stages = tst;
     long long mt = 0;
     for (int i = 0; i < g.nphase; ++i) {
       q.ph[i] = g.ph[i];
       q.ph[i].m_tile_begin = (int)mt;
-      q.tiles_x[i] = ceil_div(g.ph[i].Wp, q.tw);
-      q.tiles_y[i] = ceil_div(g.ph[i].Hp, q.th);
-      mt += (long long)g.N * q.tiles_x[i] * q.tiles_y[i];
+      mt += ceil_div64((long long)g.N * q.tiles_x[i] * q.tiles_y[i], q.mt);
       tm.w[i] = maps.w[i];
     }
     if (mt > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return SGK_EUNSUPPORTED; }
@@ -1008,7 +945,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(activations) failed (%d)", (int)r); return SGK_ECUDA; }
-    const size_t tsmem = (size_t)tst * stage_bytes + 8 * (2 * tst + 2) + 1024;
+    const size_t tsmem = (size_t)tst * tstage_bytes + 8 * (2 * tst + 2) + 1024;
     static bool tattr = false;
     if (!tattr) {
       cudaError_t e = cudaFuncSetAttribute(conv_tma_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

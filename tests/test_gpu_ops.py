@@ -314,3 +314,60 @@ def test_errors_are_loud(S):
     with pytest.raises(RuntimeError):
         S.ops.conv(torch.zeros(1, 8, 8, 3, device="cuda"), torch.zeros(4, 3, 3, 3, device="cuda"), None,
                    S.ops.ConvCfg(False, 3, 3, 1))                                  # stride 3 unsupported
+
+
+# ---------------------------------------------------------------------------------------------- tap fold / pad helpers
+def test_tap_fold_unfold_and_pad(S):
+    """sgk_tap_* and sgk_pad_nhwc (csrc/taps.cu) against direct numpy restatements of their definitions."""
+    import ctypes
+    lib = S._lib.load()
+    rng = np.random.default_rng(5)
+    N, H, W, Co, Ci, k, p = 2, 7, 9, 2, 32, 4, 2
+    Ho, Wo = H + 2 * p - k + 1, W + 2 * p - k + 1
+    st = torch.cuda.current_stream().cuda_stream
+    # weights
+    w = rng.standard_normal((Co, Ci, k, k)).astype(np.float32)
+    wt, w32 = torch.tensor(w, device="cuda"), torch.empty(32, Ci, device="cuda")
+    assert lib.sgk_tap_weight_pack(wt.data_ptr(), w32.data_ptr(), Co, Ci, k, st) == 0
+    exp = np.zeros((32, Ci), np.float32)
+    exp[:Co * k * k] = np.transpose(w, (0, 2, 3, 1)).reshape(Co * k * k, Ci)
+    np.testing.assert_array_equal(w32.cpu().numpy(), exp)
+    back = torch.empty_like(wt)
+    assert lib.sgk_tap_weight_unpack(w32.data_ptr(), back.data_ptr(), Co, Ci, k, st) == 0
+    np.testing.assert_array_equal(back.cpu().numpy(), w)
+    # fold: y = bias + sum of shifted tap planes
+    t = rng.standard_normal((N, H, W, 32)).astype(np.float32)
+    b = rng.standard_normal(Co).astype(np.float32)
+    y = torch.empty(N, Ho, Wo, Co, device="cuda")
+    assert lib.sgk_tap_fold_fwd(torch.tensor(t, device="cuda").data_ptr(), torch.tensor(b, device="cuda").data_ptr(), y.data_ptr(),
+                                N, H, W, Co, k, p, 0, 0.0, st) == 0
+    ref = np.zeros((N, Ho, Wo, Co))
+    for co in range(Co):
+        for a in range(k):
+            for bb in range(k):
+                for oy in range(Ho):
+                    iy = oy + a - p
+                    if not 0 <= iy < H:
+                        continue
+                    for ox in range(Wo):
+                        ix = ox + bb - p
+                        if 0 <= ix < W:
+                            ref[:, oy, ox, co] += t[:, iy, ix, (co * k + a) * k + bb]
+    ref += b
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    # unfold is the adjoint of fold: <fold(t), dy> == <t, unfold(dy)>
+    dy = rng.standard_normal((N, Ho, Wo, Co)).astype(np.float32)
+    g32 = torch.empty(N, H, W, 32, device="cuda")
+    assert lib.sgk_tap_unfold(torch.tensor(dy, device="cuda").data_ptr(), g32.data_ptr(), N, H, W, Co, k, p, st) == 0
+    lhs = float(((ref - b) * dy).sum())
+    rhs = float((t.astype(np.float64) * g32.cpu().numpy()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+    assert np.all(g32.cpu().numpy()[..., Co * k * k:] == 0)
+    # zero-padded copy
+    for C in (2, 3, 4):
+        x = rng.standard_normal((N, H, W, C)).astype(np.float32)
+        xp = torch.empty(N, H + 2 * p, W + 2 * p, C, device="cuda")
+        assert lib.sgk_pad_nhwc(torch.tensor(x, device="cuda").data_ptr(), xp.data_ptr(), N, H, W, C, p, st) == 0
+        np.testing.assert_array_equal(xp.cpu().numpy(), np.pad(x, ((0, 0), (p, p), (p, p), (0, 0))))
+    # rows beyond 32 are refused
+    assert lib.sgk_tap_fold_fwd(y.data_ptr(), None, y.data_ptr(), 1, 4, 4, 3, 4, 2, 0, 0.0, st) != 0
