@@ -102,6 +102,11 @@ int sgk_conv_dgrad(const SgkConvDesc* d, const float* dy, const float* w_packed_
 size_t sgk_conv_wgrad_workspace_bytes(const SgkConvDesc* d);
 int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float* dy, float* dw, float* dbias,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* Same, for a conv followed by ReLU / LeakyReLU (nn.Conv2d + nn.LeakyReLU(0.2, True), networks.py:815-818), given dy w.r.t. the
+ * ACTIVATED output y: activation backward and bias column sums are fused into the kernel's loads.  Returns
+ * SGK_EUNSUPPORTED (nothing written) for shapes without a fused kernel: run sgk_act_bwd + sgk_conv_wgrad instead. */
+int sgk_conv_wgrad_act(const SgkConvDesc* d, const float* x, const float* dy, const float* y, int act, float slope, float* dw,
+                       float* dbias, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- layout (network edges) */
 int sgk_layout_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, void* stream);

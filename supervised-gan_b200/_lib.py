@@ -41,6 +41,7 @@ SIGNATURES = {
     "sgk_conv_dgrad": (c_int, [POINTER(SgkConvDesc), P, P, P, P]),
     "sgk_conv_wgrad_workspace_bytes": (c_size_t, [POINTER(SgkConvDesc)]),
     "sgk_conv_wgrad": (c_int, [POINTER(SgkConvDesc), P, P, P, P, P, c_size_t, P]),
+    "sgk_conv_wgrad_act": (c_int, [POINTER(SgkConvDesc), P, P, P, c_int, c_float, P, P, P, c_size_t, P]),
     "sgk_layout_nchw_to_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "sgk_layout_nhwc_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "sgk_norm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
@@ -98,6 +99,9 @@ def load():
         raise RuntimeError("libsgk.so version mismatch")
     _lib = lib
     return lib
+
+
+EINVAL, EUNSUPPORTED, ECUDA, EWORKSPACE = -1, -2, -3, -4   # include/sgk.h SgkStatus
 
 
 def check(rc, what=""):

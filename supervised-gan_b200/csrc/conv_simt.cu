@@ -988,7 +988,9 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
 int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t st);
 size_t conv_wgrad_tc_workspace_bytes(const SgkConvDesc* d);
-int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* part, int ctas, cudaStream_t st);
+int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* part, int ctas, const float* y, int act, float slope,
+                   float* bias_part, cudaStream_t st);
+int launch_colsum_final(const float* part, float* out, int C, int chunks, cudaStream_t st);
 }
 
 static int conv_gather_dispatch(const SgkConvDesc* d, int op, const float* in, const float* w, const float* bias,
@@ -1023,10 +1025,45 @@ extern "C" size_t sgk_conv_wgrad_workspace_bytes(const SgkConvDesc* d) {
   size_t a = (size_t)splits * e.O * e.I * e.k * e.k * sizeof(float);
   size_t b = sgk_bias_grad_workspace_bytes((size_t)d->N * d->Hout * d->Wout, d->Cout);
   size_t c = d->precision != SGK_FP32 ? conv_wgrad_tc_workspace_bytes(d) : 0;
-  size_t dd = (size_t)3 * sm_count() * e.O * e.I * e.k * e.k * sizeof(float);   // image-edge kernels: one partial per CTA
+  size_t dd = (size_t)3 * sm_count() * e.O * (e.I * e.k * e.k + 1) * sizeof(float);   // image-edge kernels: one partial per CTA
   a = a > b ? a : b;
   a = a > c ? a : c;
   return a > dd ? a : dd;
+}
+
+// Weight (and bias) gradient of a conv whose output went through ReLU / LeakyReLU, given the gradient w.r.t. the ACTIVATED
+// output: the activation backward and the bias column sums are fused into the weight-gradient kernel's loads (saves one
+// full write + two full reads of the layer's widest tensor).  Only shapes with a fused kernel are taken (today: the
+// discriminator's 2-channel image layer, non-transposed); everything else returns SGK_EUNSUPPORTED and the caller runs
+// sgk_act_bwd + sgk_conv_wgrad.
+extern "C" int sgk_conv_wgrad_act(const SgkConvDesc* d, const float* x, const float* dy, const float* y, int act, float slope,
+                                  float* dw, float* dbias, void* workspace, size_t workspace_bytes, void* stream) {
+  SGK_CHECK_ARG(d && x && dy && y && dw && workspace, "sgk_conv_wgrad_act: null argument");
+  int rc = validate_desc(*d);
+  if (rc) return rc;
+  if (act != SGK_ACT_RELU && act != SGK_ACT_LRELU) return SGK_EUNSUPPORTED;
+  if (d->transposed) return SGK_EUNSUPPORTED;
+  EquivConv e = equiv_conv(*d);
+  const int ekey = e.k * 100 + e.k * e.I;
+  if (!(e.I == 2 && e.O >= 32 && ekey == 408)) return SGK_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = e.k * e.k * e.I;
+  const long long ntiles = (long long)ceil_div(e.Ws, EG_TW) * ceil_div(e.Hs, EG_TH) * e.N;
+  const int cgroups = ceil_div(e.O, 32);
+  long long ctas = 3LL * sm_count() / cgroups;
+  if (ctas < 1) ctas = 1;
+  if (ctas > ntiles) ctas = ntiles;
+  const size_t need = (size_t)ctas * e.O * (K + 1) * sizeof(float);
+  if (need > workspace_bytes) { set_error("sgk_conv_wgrad_act: workspace %zu < %zu", workspace_bytes, need); return SGK_EWORKSPACE; }
+  float* part = (float*)workspace;
+  float* bias_part = dbias ? part + (size_t)ctas * e.O * K : nullptr;
+  rc = edge_wgrad_tma(e, dy, x, part, (int)ctas, y, act, slope, bias_part, st);
+  if (rc) return rc;   // incl. SGK_EUNSUPPORTED (alignment): nothing has been written
+  if (dbias) {
+    rc = launch_colsum_final(bias_part, dbias, e.O, (int)ctas, st);
+    if (rc) return rc;
+  }
+  return launch_wgrad_reduce(part, dw, e.O, e.I, e.k, (int)ctas, st);
 }
 
 extern "C" int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float* dy, float* dw, float* dbias,
@@ -1066,7 +1103,7 @@ extern "C" int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float*
       q.N = e.N; q.Hg = e.Hs; q.Wg = e.Ws; q.Cm = e.O; q.Hx = e.Hb; q.Wx = e.Wb; q.Cx = e.I;
       q.k = e.k; q.s = e.s; q.off = -e.p; q.K = K; q.P = (long long)e.N * e.Hs * e.Ws; q.p_per_split = 0;
       if (ekey == 408) {
-        rc = edge_wgrad_tma(e, q.g, q.x, q.part, (int)ctas, st);
+        rc = edge_wgrad_tma(e, q.g, q.x, q.part, (int)ctas, nullptr, SGK_ACT_NONE, 0.f, nullptr, st);
         if (rc == SGK_OK) return launch_wgrad_reduce((const float*)workspace, dw, e.O, e.I, e.k, (int)ctas, st);
         if (rc != SGK_EUNSUPPORTED) return rc;
       }

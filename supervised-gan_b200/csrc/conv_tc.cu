@@ -1528,6 +1528,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int 
 
 struct EdgeWParams {
   const float* g;
+  const float* y;        // optional: activated forward output; then g is the gradient w.r.t. y and act' is applied on load
+  float* bias_part;      // optional: [gridDim.x][Cm] column sums of the (pre-activation) gradient
+  int act;
+  float slope;
   float* part;           // [gridDim.x][Cm][32]
   int N, Hg, Wg, Cm;
   int s, off, Cx;
@@ -1568,6 +1572,7 @@ edge_wgrad_tma_kernel(const __grid_constant__ EdgeWParams p, const __grid_consta
   float acc[EW_K];
 #pragma unroll
   for (int k = 0; k < EW_K; ++k) acc[k] = 0.f;
+  float bsum = 0.f;
   if (threadIdx.x == 0 && (long long)blockIdx.x < ntiles) issue(blockIdx.x, 0);
   int it = 0;
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -1581,9 +1586,22 @@ edge_wgrad_tma_kernel(const __grid_constant__ EdgeWParams p, const __grid_consta
     // G values of this warp's row segment first: they do not depend on the patch
     float gq[EW_TW];
     if (oy < p.Hg) {
-      const float* __restrict__ grow = p.g + (((long long)n * p.Hg + oy) * p.Wg) * p.Cm + m;
+      const long long rowofs = (((long long)n * p.Hg + oy) * p.Wg) * p.Cm + m;
+      const float* __restrict__ grow = p.g + rowofs;
 #pragma unroll
       for (int xl = 0; xl < EW_TW; ++xl) gq[xl] = (m < p.Cm && ox0 + xl < p.Wg) ? __ldg(grow + (long long)(ox0 + xl) * p.Cm) : 0.f;
+      if (p.y != nullptr) {
+        // fused activation backward: dpre = dy * act'(y) (ReLU / LeakyReLU: the sign of y is the sign of the pre-activation)
+        const float* __restrict__ yrow = p.y + rowofs;
+        const float neg = p.act == SGK_ACT_LRELU ? p.slope : 0.f;
+#pragma unroll
+        for (int xl = 0; xl < EW_TW; ++xl) {
+          const float yv = (m < p.Cm && ox0 + xl < p.Wg) ? __ldg(yrow + (long long)(ox0 + xl) * p.Cm) : 1.f;
+          gq[xl] *= yv > 0.f ? 1.f : neg;
+        }
+      }
+#pragma unroll
+      for (int xl = 0; xl < EW_TW; ++xl) bsum += gq[xl];
     }
     mbar_wait(bar0 + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));
     if (oy < p.Hg) {
@@ -1610,6 +1628,7 @@ edge_wgrad_tma_kernel(const __grid_constant__ EdgeWParams p, const __grid_consta
   // fixed-order reduction over the 8 warps (rows padded to 33 floats: conflict-free), one partial block per CTA
 #pragma unroll
   for (int k = 0; k < EW_K; ++k) red[((size_t)warp * 32 + lane) * 33 + k] = acc[k];
+  red[((size_t)warp * 32 + lane) * 33 + 32] = bsum;   // the padding column carries the bias-gradient partial
   __syncthreads();
   {
     // 256 threads: thread -> (channel lane, 4 of the 32 k's)
@@ -1625,12 +1644,19 @@ edge_wgrad_tma_kernel(const __grid_constant__ EdgeWParams p, const __grid_consta
         for (int wq = 0; wq < 8; ++wq) sacc += red[((size_t)wq * 32 + cl) * 33 + k];
         dst[k] = sacc;
       }
+      if (kq == 0 && p.bias_part != nullptr) {
+        float sb = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) sb += red[((size_t)wq * 32 + cl) * 33 + 32];
+        p.bias_part[(long long)blockIdx.x * p.Cm + mm] = sb;
+      }
     }
   }
 }
 
 // returns SGK_EUNSUPPORTED when the shape / alignment does not fit (the caller keeps its own kernel)
-int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* part, int ctas, cudaStream_t st) {
+int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* part, int ctas, const float* y, int act, float slope,
+                   float* bias_part, cudaStream_t st) {
   static const bool on = !(getenv("SGK_EDGE_TMA") != nullptr && atoi(getenv("SGK_EDGE_TMA")) == 0);
   if (!on || e.k != 4 || e.I != 2 || e.s > 2) return SGK_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || ((long long)e.Wb * e.I * 4) % 16 != 0 || (e.p * e.I * 4) % 16 != 0 ||
@@ -1639,7 +1665,7 @@ int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* pa
   EncodeTiledFn encode = get_encode_tiled();
   if (!encode) return SGK_EUNSUPPORTED;
   EdgeWParams q{};
-  q.g = g; q.part = part;
+  q.g = g; q.part = part; q.y = y; q.act = act; q.slope = slope; q.bias_part = bias_part;
   q.N = e.N; q.Hg = e.Hs; q.Wg = e.Ws; q.Cm = e.O; q.s = e.s; q.off = -e.p; q.Cx = e.I;
   q.tiles_x = ceil_div(e.Ws, EW_TW); q.tiles_y = ceil_div(e.Hs, EW_TH);
   q.PH = (EW_TH - 1) * e.s + e.k;

@@ -272,6 +272,15 @@ extern "C" int sgk_bias_grad(const float* dy, float* db, size_t rows, int C, voi
   return SGK_OK;
 }
 
+namespace sgk {
+// out[c] = sum_k part[k][c] (fixed order): shared with kernels that produce their own per-CTA column partials
+int launch_colsum_final(const float* part, float* out, int C, int chunks, cudaStream_t st) {
+  colsum_final_kernel<<<ceil_div(C, 4), 128, 0, st>>>(part, out, C, chunks);
+  SGK_LAUNCH_CHECK("colsum_final_kernel");
+  return SGK_OK;
+}
+}  // namespace sgk
+
 extern "C" int sgk_concat2_nhwc(const float* a, int Ca, const float* b, int Cb, float* out, size_t pixels, void* stream) {
   SGK_CHECK_ARG(a && b && out && Ca > 0 && Cb > 0, "sgk_concat2_nhwc: bad argument");
   long long total = (long long)pixels * (Ca + Cb);

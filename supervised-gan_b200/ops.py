@@ -257,11 +257,29 @@ class _ConvFn(torch.autograd.Function):
         weight = ctx.weight_ref
         dy = _chk(dy, "conv grad")
         st = _stream()
+        gx = gw = gb = None
+        if (ctx.act in (L.ACT_RELU, L.ACT_LRELU) and ctx.descp is not None and not ctx.needs_input_grad[0]
+                and ctx.needs_input_grad[1]):
+            # image layer in the D phase (no input gradient): activation backward + bias column sums fused into the
+            # weight-gradient kernel's loads
+            wdesc = ctx.descp
+            want_b = ctx.has_bias and ctx.needs_input_grad[2] and not ctx.bias_grad_zero
+            gw = torch.empty_like(weight)
+            gbf = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device) if want_b else None
+            ws = _ws(lib.sgk_conv_wgrad_workspace_bytes(ctypes.byref(wdesc)), dy.device)
+            rc = _timed(_conv_tag("wgrad", wdesc), _conv_flops(wdesc), lambda: lib.sgk_conv_wgrad_act(
+                ctypes.byref(wdesc), _p(x), _p(dy), _p(y), ctx.act, ctx.slope, _p(gw), _p(gbf), _p(ws), ws.numel(), st))
+            if rc == 0:
+                if ctx.has_bias and ctx.needs_input_grad[2]:
+                    gb = gbf if want_b else torch.zeros(desc.Cout, dtype=torch.float32, device=dy.device)
+                return None, gw, gb, None, None, None, None
+            if rc != L.EUNSUPPORTED:
+                L.check(rc, "conv_wgrad_act")
+            gw = None
         if ctx.act != L.ACT_NONE:
             dpre = torch.empty_like(dy)
             L.check(lib.sgk_act_bwd(_p(dy), _p(y), _p(dpre), dy.numel(), ctx.act, ctx.slope, st), "act_bwd")
             dy = dpre
-        gx = gw = gb = None
         if ctx.tap:
             desc1, _, _, wpd = cfg.tap_weights(weight.detach(), x.shape)
             g32 = torch.empty((desc.N, desc.Hin, desc.Win, 32), dtype=torch.float32, device=dy.device)
