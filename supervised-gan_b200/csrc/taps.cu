@@ -36,12 +36,14 @@ __global__ void tap_weight_unpack_kernel(const float* __restrict__ dw32, float* 
 
 // one thread per output element; the k*k reads of one output are 128-B rows apart but neighbouring threads read
 // neighbouring rows, and t (a few MB) is L2 resident right after the 1x1 conv wrote it
+// (index type I: 32-bit whenever the element count allows -- 64-bit div/mod chains cost more than the kernel's real work)
+template <typename I>
 __global__ void tap_fold_kernel(const float* __restrict__ t, const float* __restrict__ bias, float* __restrict__ y, int N, int H,
                                 int W, int Ho, int Wo, int Cout, int k, int pad, int act, float slope) {
-  const long long total = (long long)N * Ho * Wo * Cout;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const I total = (I)N * Ho * Wo * Cout;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cout);
-    long long pix = i / Cout;
+    I pix = i / Cout;
     const int ox = (int)(pix % Wo);
     pix /= Wo;
     const int oy = (int)(pix % Ho);
@@ -61,12 +63,13 @@ __global__ void tap_fold_kernel(const float* __restrict__ t, const float* __rest
 }
 
 // one thread per (input pixel, r): 128-B coalesced rows of G32
+template <typename I>
 __global__ void tap_unfold_kernel(const float* __restrict__ dy, float* __restrict__ g32, int N, int H, int W, int Ho, int Wo,
                                   int Cout, int k, int pad) {
-  const long long total = (long long)N * H * W * TAP_ROWS;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const I total = (I)N * H * W * TAP_ROWS;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int r = (int)(i & (TAP_ROWS - 1));
-    long long pix = i >> 5;
+    I pix = i >> 5;
     const int ix = (int)(pix % W);
     pix /= W;
     const int iy = (int)(pix % H);
@@ -84,14 +87,14 @@ __global__ void tap_unfold_kernel(const float* __restrict__ dy, float* __restric
 
 // zero-padded copy of an NHWC tensor (the im2col-by-TMA path of conv_tc.cu reads image layers from a padded buffer so that
 // every patch is in bounds); one thread per output pixel channel-vector
-template <int V>
+template <int V, typename I>
 __global__ void pad_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int pad) {
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const int cv = C / V;
-  const long long total = (long long)N * Hp * Wp * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const I total = (I)N * Hp * Wp * cv;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int c = (int)(i % cv);
-    long long pix = i / cv;
+    I pix = i / cv;
     const int px = (int)(pix % Wp);
     pix /= Wp;
     const int py = (int)(pix % Hp);
@@ -151,8 +154,11 @@ extern "C" int sgk_tap_fold_fwd(const float* t, const float* bias, float* y, int
   if (int rc = tap_check(Cout, k, pad)) return rc;
   const int Ho = H + 2 * pad - k + 1, Wo = W + 2 * pad - k + 1;
   if (Ho <= 0 || Wo <= 0) { set_error("sgk_tap_fold_fwd: empty output"); return SGK_EINVAL; }
-  tap_fold_kernel<<<tap_blocks((long long)N * Ho * Wo * Cout), 256, 0, (cudaStream_t)stream>>>(t, bias, y, N, H, W, Ho, Wo, Cout, k,
-                                                                                              pad, act, slope);
+  const long long tot = (long long)N * Ho * Wo * Cout;
+  if (tot < (1LL << 30) && (long long)N * H * W * TAP_ROWS < (1LL << 31))
+    tap_fold_kernel<int><<<tap_blocks(tot), 256, 0, (cudaStream_t)stream>>>(t, bias, y, N, H, W, Ho, Wo, Cout, k, pad, act, slope);
+  else
+    tap_fold_kernel<long long><<<tap_blocks(tot), 256, 0, (cudaStream_t)stream>>>(t, bias, y, N, H, W, Ho, Wo, Cout, k, pad, act, slope);
   SGK_LAUNCH_CHECK("tap_fold_kernel");
   return SGK_OK;
 }
@@ -162,8 +168,11 @@ extern "C" int sgk_tap_unfold(const float* dy, float* g32, int N, int H, int W, 
   if (int rc = tap_check(Cout, k, pad)) return rc;
   const int Ho = H + 2 * pad - k + 1, Wo = W + 2 * pad - k + 1;
   if (Ho <= 0 || Wo <= 0) { set_error("sgk_tap_unfold: empty output"); return SGK_EINVAL; }
-  tap_unfold_kernel<<<tap_blocks((long long)N * H * W * TAP_ROWS), 256, 0, (cudaStream_t)stream>>>(dy, g32, N, H, W, Ho, Wo, Cout, k,
-                                                                                                  pad);
+  const long long tot = (long long)N * H * W * TAP_ROWS;
+  if (tot < (1LL << 30))
+    tap_unfold_kernel<int><<<tap_blocks(tot), 256, 0, (cudaStream_t)stream>>>(dy, g32, N, H, W, Ho, Wo, Cout, k, pad);
+  else
+    tap_unfold_kernel<long long><<<tap_blocks(tot), 256, 0, (cudaStream_t)stream>>>(dy, g32, N, H, W, Ho, Wo, Cout, k, pad);
   SGK_LAUNCH_CHECK("tap_unfold_kernel");
   return SGK_OK;
 }
@@ -174,9 +183,16 @@ extern "C" int sgk_pad_nhwc(const float* x, float* y, int N, int H, int W, int C
   cudaStream_t st = (cudaStream_t)stream;
   const bool a16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
   const bool a8 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 7) == 0;
-  if (C % 4 == 0 && a16) pad_nhwc_kernel<4><<<tap_blocks(pix * (C / 4)), 256, 0, st>>>(x, y, N, H, W, C, pad);
-  else if (C % 2 == 0 && a8) pad_nhwc_kernel<2><<<tap_blocks(pix * (C / 2)), 256, 0, st>>>(x, y, N, H, W, C, pad);
-  else pad_nhwc_kernel<1><<<tap_blocks(pix * C), 256, 0, st>>>(x, y, N, H, W, C, pad);
+  const bool small = pix * C < (1LL << 30);
+#define SGK_PAD_LAUNCH(V_)                                                                                       \
+  {                                                                                                              \
+    if (small) pad_nhwc_kernel<V_, int><<<tap_blocks(pix * (C / V_)), 256, 0, st>>>(x, y, N, H, W, C, pad);      \
+    else pad_nhwc_kernel<V_, long long><<<tap_blocks(pix * (C / V_)), 256, 0, st>>>(x, y, N, H, W, C, pad);      \
+  }
+  if (C % 4 == 0 && a16) SGK_PAD_LAUNCH(4)
+  else if (C % 2 == 0 && a8) SGK_PAD_LAUNCH(2)
+  else SGK_PAD_LAUNCH(1)
+#undef SGK_PAD_LAUNCH
   SGK_LAUNCH_CHECK("pad_nhwc_kernel");
   return SGK_OK;
 }
