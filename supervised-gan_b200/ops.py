@@ -175,6 +175,15 @@ class ConvCfg:
         cout, cin = weight.shape[0], weight.shape[1]
         return cin == 2 and cout % 32 == 0 and x_shape[2] % 2 == 0
 
+    # ---- the mirror case: ConvTranspose2d(.., 2, k4 s2 p>0) producing the 2-channel image (generator's last layer,
+    # networks.py:527-529).  Its dgrad is a direct conv over dy and its wgrad gathers dy: both run from a zero-padded dy
+    # with pad = 0 (ConvT with pad 0 has exactly the padded output size), which makes them eligible for the TMA-fed kernels.
+    def padded_image_output(self, weight, desc):
+        if not self.transposed or self.stride != 2 or self.k != 4 or self.pad <= 0 or _precision == L.FP32 or not _im2col:
+            return False
+        cin, cout = weight.shape[0], weight.shape[1]
+        return cout == 2 and cin % 32 == 0 and desc.Wout % 2 == 0
+
     # ---- tap-folded evaluation of thin-output stride-1 convs (csrc/taps.cu): Cout*k*k <= 32 rows of a 1x1 conv
     def tap_folded(self, weight, x_shape):
         if self.transposed or self.stride != 1 or self.k == 1 or _precision == L.FP32 or not _tap_fold:
@@ -304,11 +313,19 @@ class _ConvFn(torch.autograd.Function):
                     ws = _ws(lib.sgk_bias_grad_workspace_bytes(rows, desc.Cout), dy.device)
                     L.check(lib.sgk_bias_grad(_p(dy), _p(gb), rows, desc.Cout, _p(ws), ws.numel(), st), "bias_grad")
             return gx, gw, gb, None, None, None, None
+        bdesc = desc          # desc the backward kernels see; for image-producing ConvT layers dy is zero-padded and pad = 0
+        if cfg.padded_image_output(weight, desc):
+            pd = desc.pad
+            dyp = torch.empty((desc.N, desc.Hout + 2 * pd, desc.Wout + 2 * pd, desc.Cout), dtype=torch.float32, device=dy.device)
+            L.check(lib.sgk_pad_nhwc(_p(dy), _p(dyp), desc.N, desc.Hout, desc.Wout, desc.Cout, pd, st), "pad_nhwc")
+            bdesc = L.SgkConvDesc(desc.N, desc.Cin, desc.Hin, desc.Win, desc.Cout, desc.Hout + 2 * pd, desc.Wout + 2 * pd,
+                                  desc.k, desc.stride, 0, 1, desc.precision)
+            dy = dyp
         if ctx.needs_input_grad[0]:
             gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dy.device)
             wp = cfg.packed(weight, desc, L.OP_DGRAD)
-            L.check(_timed(_conv_tag("dgrad", desc), _conv_flops(desc), lambda: lib.sgk_conv_dgrad(
-                ctypes.byref(desc), _p(dy), _p(wp), _p(gx), st)), "conv_dgrad")
+            L.check(_timed(_conv_tag("dgrad", bdesc), _conv_flops(desc), lambda: lib.sgk_conv_dgrad(
+                ctypes.byref(bdesc), _p(dy), _p(wp), _p(gx), st)), "conv_dgrad")
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if want_b and ctx.bias_grad_zero:
             gb = torch.zeros(desc.Cout, dtype=torch.float32, device=dy.device)
@@ -317,7 +334,7 @@ class _ConvFn(torch.autograd.Function):
             gw = torch.empty_like(weight)
             if want_b:
                 gb = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device)
-            wdesc = ctx.descp if ctx.descp is not None else desc
+            wdesc = ctx.descp if ctx.descp is not None else bdesc
             nbytes = lib.sgk_conv_wgrad_workspace_bytes(ctypes.byref(wdesc))
             ws = _ws(nbytes, dy.device)
             L.check(_timed(_conv_tag("wgrad", wdesc), _conv_flops(wdesc), lambda: lib.sgk_conv_wgrad(

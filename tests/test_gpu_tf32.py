@@ -53,6 +53,8 @@ TC_CASES = [  # transposed, N, Cin, Cout, H, W, k, s, p  (all channel counts mul
     # tap-folded heads (Cout*k*k <= 32, stride 1): 1x1 conv + fold (csrc/taps.cu)
     # image layers: padded copy + im2col-by-TMA (2-channel input, k4 s2, even width)
     (0, 3, 2, 64, 64, 64, 4, 2, 2), (0, 2, 2, 32, 34, 130, 4, 2, 1),
+    # image-producing ConvT (generator's last layer): dgrad / wgrad from a zero-padded dy with pad = 0
+    (1, 2, 32, 2, 32, 24, 4, 2, 1), (1, 1, 64, 2, 16, 16, 4, 2, 1),
     (0, 2, 256, 2, 19, 17, 4, 1, 2), (0, 3, 256, 1, 66, 66, 4, 1, 2), (0, 1, 32, 3, 9, 12, 3, 1, 0),
 ]
 
