@@ -158,7 +158,12 @@ def run_ours(args):
     if world > 1:
         sdist.broadcast_parameters(list(m.netG.parameters()) + list(m.netG.buffers()) +
                                    [p for d in m.netD for p in d.parameters()])
-        m.grad_sync = sdist.GradSync(world)
+        if os.environ.get("SGK_OVERLAP_COMM", "1") != "0":
+            # one bucket per discriminator scale (their backward passes run one after the other), two for the generator
+            m.grad_sync = sdist.OverlappedGradSync(world, {"D": [list(d.parameters()) for d in m.netD],
+                                                           "G": sdist.size_split(list(m.netG.parameters()))})
+        else:
+            m.grad_sync = sdist.GradSync(world)
 
     gen = torch.Generator().manual_seed(99 + rank)
     host_batches = [(torch.rand(B, 3, 512, 512, generator=gen) * 2 - 1).pin_memory() for _ in range(2)]

@@ -66,3 +66,100 @@ class GradSync:
         for p, lay in zip(params, layout):
             if lay is not None:
                 p.grad = flat[lay[0]:lay[0] + lay[1]].view_as(p)
+
+
+class OverlappedGradSync(GradSync):
+    """GradSync whose all-reduces start DURING backward (north_star: "gradient buckets all-reduced by NCCL over NVLink
+    overlapped with backward").
+
+    `buckets` maps a phase tag to a list of parameter lists, e.g. {"D": [params of D_scale1, D_scale2, D_scale4],
+    "G": [late layers, early layers]}.  `arm(tag)` is called right before the phase's backward; post-accumulate-grad hooks
+    count the bucket's parameters down and, when the last gradient of a bucket has been produced, pack it and launch an
+    asynchronous all-reduce (NCCL runs it on its own stream, ordered after the packing kernel by an event) while autograd
+    keeps executing the remaining layers.  `__call__(params, tag)` -- the same call the model makes for the plain
+    GradSync -- launches whatever did not complete on its own (parameters without gradient), waits for all collectives
+    (a stream dependency, no host block with NCCL) and re-points `.grad` at the reduced bucket slices.
+    Everything is capturable in the step's CUDA graph: the collectives become parallel branches of the graph."""
+
+    def __init__(self, world, buckets, packer=cuda_packer, group=None):
+        super().__init__(world, packer, group)
+        self.buckets = {tag: [[p for p in plist if p.requires_grad] for plist in bl] for tag, bl in buckets.items()}
+        self._owner = {}
+        self._active = None
+        self._count, self._launched, self._inflight = [], [], []
+        self._handles = []
+        for tag, bl in self.buckets.items():
+            for bi, plist in enumerate(bl):
+                for p in plist:
+                    self._owner[id(p)] = (tag, bi)
+                    self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def arm(self, tag):
+        if tag not in self.buckets:
+            self._active = None
+            return
+        self._active = tag
+        self._count = [len(plist) for plist in self.buckets[tag]]
+        self._launched = [False] * len(self._count)
+        self._inflight = []
+
+    def _hook(self, p):
+        if self._active is None:
+            return
+        tag, bi = self._owner.get(id(p), (None, None))
+        if tag != self._active or self._launched[bi]:
+            return
+        self._count[bi] -= 1
+        if self._count[bi] == 0:
+            self._launch(tag, bi)
+
+    def _launch(self, tag, bi):
+        self._launched[bi] = True
+        params = self.buckets[tag][bi]
+        layout, total = bucket_layout(params)
+        if total == 0:
+            return
+        dev = next(p.grad.device for p in params if p.grad is not None)
+        key = (tag, bi)
+        flat = self.buffers.get(key)
+        if flat is None or flat.numel() != total or flat.device != dev:
+            flat = torch.empty(total, dtype=torch.float32, device=dev)
+            self.buffers[key] = flat
+        grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in params if p.grad is not None]
+        self.packer(grads, flat)
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._inflight.append((work, params, layout, flat))
+
+    def __call__(self, params, tag):
+        if self._active != tag:
+            return super().__call__(params, tag)       # not armed for this phase: one bucket, synchronous
+        for bi, done in enumerate(self._launched):
+            if not done:
+                self._launch(tag, bi)
+        covered = set()
+        for work, plist, layout, flat in self._inflight:
+            work.wait()
+            for p, lay in zip(plist, layout):
+                covered.add(id(p))
+                if lay is not None:
+                    p.grad = flat[lay[0]:lay[0] + lay[1]].view_as(p)
+        self._inflight, self._active = [], None
+        rest = [p for p in params if id(p) not in covered and p.grad is not None]
+        if rest:
+            super().__call__(rest, tag + ":rest")     # parameters outside every bucket
+
+
+def size_split(params, first_fraction=0.25):
+    """Two buckets for a network whose gradients appear last-layer-first: (late layers holding ~first_fraction of the
+    elements, the rest).  The late bucket's all-reduce overlaps the backward of the early layers."""
+    params = [p for p in params if p.requires_grad]
+    total = sum(p.numel() for p in params)
+    late, acc = [], 0
+    for p in reversed(params):
+        if acc >= first_fraction * total and late:
+            break
+        late.append(p)
+        acc += p.numel()
+    late_ids = {id(p) for p in late}
+    early = [p for p in params if id(p) not in late_ids]
+    return [late[::-1], early] if early else [late[::-1]]

@@ -216,6 +216,8 @@ class FCGANModel(object):
         self.forward()
         for _ in range(self.opt.n_update_D):
             self.optimizer_D.zero_grad(set_to_none=True)
+            if self.grad_sync is not None and hasattr(self.grad_sync, "arm"):
+                self.grad_sync.arm("D")           # bucketed all-reduces start while backward is still running
             self.backward_D()
             if self.grad_sync is not None:
                 self.grad_sync(self.params_D, "D")
@@ -224,6 +226,8 @@ class FCGANModel(object):
                 self.sample_noise()
         for _ in range(self.opt.n_update_G):
             self.optimizer_G.zero_grad(set_to_none=True)
+            if self.grad_sync is not None and hasattr(self.grad_sync, "arm"):
+                self.grad_sync.arm("G")
             self.backward_G()
             if self.grad_sync is not None:
                 self.grad_sync(self.params_G, "G")

@@ -84,3 +84,72 @@ def test_grad_sync_world2_gloo():
         assert p.exitcode == 0
     got = sorted(q.get(timeout=5) for _ in range(world))
     assert got == [(0, "ok"), (1, "ok")]
+
+
+def _worker_overlap(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from supervised_gan_b200 import dist as sdist
+    torch.manual_seed(0)
+    # two "discriminators" and a 3-layer "generator"; one frozen parameter (like the Gaussian pyramid filter)
+    d1 = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(4))]
+    d2 = [torch.nn.Parameter(torch.randn(2, 3)), torch.nn.Parameter(torch.randn(2), requires_grad=False)]
+    g = [torch.nn.Parameter(torch.randn(3, 3)), torch.nn.Parameter(torch.randn(3, 3)), torch.nn.Parameter(torch.randn(3, 3))]
+    sdist.broadcast_parameters(d1 + d2 + g)
+    gb = sdist.size_split(g, 0.3)
+    assert [len(b) for b in gb] == [1, 2] and gb[0][0] is g[2]          # late layer first
+    sync = sdist.OverlappedGradSync(world, {"D": [d1, d2], "G": gb}, packer=_torch_packer)
+    torch.manual_seed(100 + rank)
+    x = torch.randn(5, 3)
+
+    def loss_d():
+        return (x @ d1[0].t() + d1[1]).pow(2).sum() + ((x @ d2[0].t()) * d2[1]).sum()
+
+    def loss_g():
+        return (((x @ g[0]) @ g[1]) @ g[2]).pow(2).sum()
+
+    # reference: plain local gradients summed over ranks
+    for ps, fn, tag in ((d1 + d2, loss_d, "D"), (g, loss_g, "G")):
+        for p in ps:
+            p.grad = None
+        fn().backward()
+        local = [None if p.grad is None else p.grad.clone() for p in ps]
+        for p in ps:
+            p.grad = None
+        launched_during_backward = []
+        sync.arm(tag)
+        fn().backward()
+        launched_during_backward = list(sync._launched)
+        sync(ps, tag)
+        assert all(launched_during_backward), "every bucket must have been launched from the autograd hooks"
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [None if t is None else t.tolist() for t in local])
+        for i, p in enumerate(ps):
+            if local[i] is None:
+                assert p.grad is None
+                continue
+            expect = sum(torch.tensor(gathered[r][i]) for r in range(world))
+            assert torch.allclose(p.grad, expect, atol=1e-5), (tag, i)
+    # an un-armed call degrades to the single synchronous bucket
+    for p in g:
+        p.grad = torch.ones_like(p) * (rank + 1)
+    sync(g, "G")
+    assert torch.allclose(g[0].grad, torch.full((3, 3), float(sum(range(1, world + 1)))))
+    dist.destroy_process_group()
+    q.put((rank, "ok"))
+
+
+def test_overlapped_grad_sync_world2_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_overlap, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(world))
+    assert got == [(0, "ok"), (1, "ok")]
