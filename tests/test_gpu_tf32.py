@@ -152,3 +152,72 @@ def test_image_layer_fused_act_wgrad(S, act):
     dw, db = O.conv2d_wgrad(dpre, x, w.shape, s, p)
     assert rel(wt.grad.cpu().numpy(), dw) <= 1e-4
     assert rel(bt.grad.cpu().numpy(), db) <= 1e-4
+
+
+def _grad_metrics(net, sd64):
+    out = {}
+    scale = max(float(v.grad.abs().max()) for v in sd64.values() if getattr(v, "grad", None) is not None)
+    for k, p in net.named_parameters():
+        if p.grad is None or sd64[k].grad is None:
+            continue
+        ref = sd64[k].grad.numpy().ravel()
+        got = p.grad.cpu().double().numpy().ravel()
+        if np.abs(ref).max() < 1e-9 * scale:
+            # conv biases feeding a norm: mathematically zero (fp64 leaves rounding noise, we emit exact zeros)
+            assert np.abs(got).max() <= 1e-6 * scale, k
+            continue
+        cos = float(got @ ref / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+        l2 = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        out[k] = (cos, l2)
+    return out
+
+
+def _as64(sd):
+    return {k: (v.detach().cpu().double().requires_grad_(True) if v.is_floating_point() else v.detach().cpu().clone())
+            for k, v in sd.items()}
+
+
+def test_unet128_real_width_tf32_vs_fp64(S):
+    """U-Net 128 at ngf 32 (every conv on the tensor-core path, spatial sizes 64..1) vs the fp64 oracle on the same weights:
+    output <= 5e-3 abs, parameter gradients cosine >= 0.98 / relative L2 <= 0.2 (skip-connection nets amplify the tf32
+    activation-kink flips more than the plain generator; fp32 mode is held to 1e-3 by test_gpu_nets)."""
+    nw = S.networks
+    torch.manual_seed(21)
+    U = nw.define_G(2, 1, 32, "unet_128", "instance", False, gpu_ids=[])
+    sd64 = _as64(U.state_dict())
+    x = torch.randn(2, 2, 128, 128)
+    proj = torch.randn(2, 1, 128, 128)
+    y64 = ON.unet_generator(sd64, x.double(), num_downs=7)
+    (y64 * proj.double()).sum().backward()
+    U.cuda()
+    y = U(x.cuda())
+    (y * proj.cuda()).sum().backward()
+    assert np.abs(y.detach().cpu().double().numpy() - y64.detach().numpy()).max() <= 5e-3
+    m = _grad_metrics(U, sd64)
+    assert len(m) >= 12
+    bad = {k: v for k, v in m.items() if not (v[0] >= 0.98 and v[1] <= 0.2)}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("mode,nb", [("bilinear", 2), ("convt", 1)])
+def test_crn_real_width_tf32_vs_fp64(S, mode, nb):
+    """CRN at ngf 32, 128x128 labels, vs the fp64 oracle (gradient bounds as in the U-Net test; output <= 1e-2 abs: twelve to
+    eighteen tf32 convs in series, each renormalised by an InstanceNorm)."""
+    nw = S.networks
+    torch.manual_seed(22)
+    C = nw.define_G(2, 1, 32, "crn", "instance", False, n_layers_G=5, noise_nc=8, upsample_mode=mode, n_layers_CRN_block=nb,
+                    gpu_ids=[])
+    sd64 = _as64(C.state_dict())
+    label = torch.randn(2, 2, 128, 128)
+    noise = torch.randn(2, 8, 2, 2)
+    proj = torch.randn(2, 1, 128, 128)
+    y64 = ON.crn_generator(sd64, label.double(), noise.double(), upsample_mode=mode, n_layers_block=nb)
+    (y64 * proj.double()).sum().backward()
+    C.cuda()
+    y = C(label.cuda(), noise.cuda())
+    (y * proj.cuda()).sum().backward()
+    assert np.abs(y.detach().cpu().double().numpy() - y64.detach().numpy()).max() <= 1e-2
+    m = _grad_metrics(C, sd64)
+    assert len(m) >= 10
+    bad = {k: v for k, v in m.items() if not (v[0] >= 0.98 and v[1] <= 0.2)}
+    assert not bad, bad
