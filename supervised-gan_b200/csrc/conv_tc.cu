@@ -816,6 +816,14 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
     if (g.Co > 16) return SGK_EUNSUPPORTED;
     BN = 16;
   }
+  // Small grids (17x17, 8x8 ... layers): with the widest N tile there are fewer CTAs than SMs and each one streams its
+  // whole K loop through a single SM's L2 port; narrower N tiles spread the same traffic over more SMs.
+  {
+    static const bool narrow = !(getenv("SGK_TC_NARROW") != nullptr && atoi(getenv("SGK_TC_NARROW")) == 0);
+    long long mtiles = 0;
+    for (int i = 0; i < g.nphase; ++i) mtiles += ceil_div64((long long)g.N * g.ph[i].Hp * g.ph[i].Wp, TC_BM);
+    while (narrow && BN > 32 && mtiles * (g.Co / BN) < sm_count()) BN >>= 1;
+  }
   // K blocks: 32 channels of one tap, or -- thin inputs -- 32 flattened (tap, channel) slots
   int cs = 0;
   if ((g.Cg % 32) != 0) {
