@@ -1548,7 +1548,8 @@ struct EdgeWParams {
   uint32_t buf_stride;   // bytes between the two patch buffers (128-B multiple)
 };
 
-template <int S>   // conv stride: patch geometry is compile-time so that every patch read is base + immediate
+template <int S, bool FUSED>   // conv stride (patch geometry is compile-time: every patch read is base + immediate);
+                               // FUSED: activation backward + bias column sums on the G loads
 __global__ void __launch_bounds__(256, 3)
 edge_wgrad_tma_kernel(const __grid_constant__ EdgeWParams p, const __grid_constant__ CUtensorMap xmap) {
   constexpr int ROWF = ((EW_TW - 1) * S + 4) * 2, XSTEP = S * 2;
@@ -1591,46 +1592,57 @@ edge_wgrad_tma_kernel(const __grid_constant__ EdgeWParams p, const __grid_consta
     const int r2 = (int)(t - (long long)n * per_img);
     const int tyi = r2 / p.tiles_x, txi = r2 - tyi * p.tiles_x;
     const int oy = tyi * EW_TH + warp, ox0 = txi * EW_TW;
-    // G values of this warp's row segment first: they do not depend on the patch
-    float gq[EW_TW];
+    // two halves of 16 pixels: 16 G values (+ 16 y values when the activation backward is fused) are loaded at once,
+    // which keeps acc[32] + gq[16] in registers without spills
+    bool waited = false;
     if (oy < p.Hg) {
       const long long rowofs = (((long long)n * p.Hg + oy) * p.Wg) * p.Cm + m;
       const float* __restrict__ grow = p.g + rowofs;
-#pragma unroll
-      for (int xl = 0; xl < EW_TW; ++xl) gq[xl] = (m < p.Cm && ox0 + xl < p.Wg) ? __ldg(grow + (long long)(ox0 + xl) * p.Cm) : 0.f;
-      if (p.y != nullptr) {
-        // fused activation backward: dpre = dy * act'(y) (ReLU / LeakyReLU: the sign of y is the sign of the pre-activation)
-        const float* __restrict__ yrow = p.y + rowofs;
-        const float neg = p.act == SGK_ACT_LRELU ? p.slope : 0.f;
-#pragma unroll
-        for (int xl = 0; xl < EW_TW; ++xl) {
-          const float yv = (m < p.Cm && ox0 + xl < p.Wg) ? __ldg(yrow + (long long)(ox0 + xl) * p.Cm) : 1.f;
-          gq[xl] *= yv > 0.f ? 1.f : neg;
-        }
-      }
-#pragma unroll
-      for (int xl = 0; xl < EW_TW; ++xl) bsum += gq[xl];
-    }
-    mbar_wait(bar0 + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));
-    if (oy < p.Hg) {
+      const float* __restrict__ yrow = FUSED ? p.y + rowofs : nullptr;
+      const float neg = p.act == SGK_ACT_LRELU ? p.slope : 0.f;
       const float* patch = reinterpret_cast<const float*>(gen + (uint32_t)buf * p.buf_stride);
       const float* prow = patch + (warp * S) * ROWF;
 #pragma unroll
-      for (int xl = 0; xl < EW_TW; ++xl) {
-        const float gv = gq[xl];
-        const float* pp0 = prow + xl * XSTEP;
+      for (int half = 0; half < 2; ++half) {
+        constexpr int HW_ = EW_TW / 2;
+        const int xb = ox0 + half * HW_;
+        float gq[HW_];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int xl = 0; xl < HW_; ++xl) gq[xl] = (m < p.Cm && xb + xl < p.Wg) ? __ldg(grow + (long long)(xb + xl) * p.Cm) : 0.f;
+        if constexpr (FUSED) {
+          // fused activation backward: dpre = dy * act'(y) (ReLU / LeakyReLU: sign(y) = sign of the pre-activation)
 #pragma unroll
-          for (int r = 0; r < 8; r += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(pp0 + a * ROWF + r);
-            acc[a * 8 + r + 0] = fmaf(gv, v.x, acc[a * 8 + r + 0]);
-            acc[a * 8 + r + 1] = fmaf(gv, v.y, acc[a * 8 + r + 1]);
-            acc[a * 8 + r + 2] = fmaf(gv, v.z, acc[a * 8 + r + 2]);
-            acc[a * 8 + r + 3] = fmaf(gv, v.w, acc[a * 8 + r + 3]);
+          for (int xl = 0; xl < HW_; ++xl) {
+            const float yv = (m < p.Cm && xb + xl < p.Wg) ? __ldg(yrow + (long long)(xb + xl) * p.Cm) : 1.f;
+            gq[xl] *= yv > 0.f ? 1.f : neg;
           }
+        }
+        if constexpr (FUSED) {
+#pragma unroll
+          for (int xl = 0; xl < HW_; ++xl) bsum += gq[xl];
+        }
+        if (!waited) {
+          mbar_wait(bar0 + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));
+          waited = true;
+        }
+#pragma unroll
+        for (int xl = 0; xl < HW_; ++xl) {
+          const float gv = gq[xl];
+          const float* pp0 = prow + (half * HW_ + xl) * XSTEP;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int r = 0; r < 8; r += 4) {
+              const float4 v = *reinterpret_cast<const float4*>(pp0 + a * ROWF + r);
+              acc[a * 8 + r + 0] = fmaf(gv, v.x, acc[a * 8 + r + 0]);
+              acc[a * 8 + r + 1] = fmaf(gv, v.y, acc[a * 8 + r + 1]);
+              acc[a * 8 + r + 2] = fmaf(gv, v.z, acc[a * 8 + r + 2]);
+              acc[a * 8 + r + 3] = fmaf(gv, v.w, acc[a * 8 + r + 3]);
+            }
+        }
       }
     }
+    if (!waited) mbar_wait(bar0 + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));   // keep the barrier phase in step
     __syncthreads();   // patch[buf] fully consumed
   }
   // fixed-order reduction over the 8 warps (rows padded to 33 floats: conflict-free), one partial block per CTA
@@ -1691,14 +1703,22 @@ int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* pa
   const size_t smem = 2 * (size_t)q.buf_stride + 16 + (size_t)8 * 32 * 33 * sizeof(float) + 128;
   static bool attr = false;
   if (!attr) {
-    cudaError_t ce = cudaFuncSetAttribute(edge_wgrad_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(edge_wgrad_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t ce = cudaFuncSetAttribute(edge_wgrad_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(edge_wgrad_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(edge_wgrad_tma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(edge_wgrad_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(edge_wgrad_tma_kernel)");
     attr = true;
   }
   dim3 grid((unsigned)ctas, (unsigned)ceil_div(e.O, 32));
-  if (e.s == 1) edge_wgrad_tma_kernel<1><<<grid, 256, smem, st>>>(q, xmap);
-  else edge_wgrad_tma_kernel<2><<<grid, 256, smem, st>>>(q, xmap);
+  const bool fused = y != nullptr;
+  if (e.s == 1) {
+    if (fused) edge_wgrad_tma_kernel<1, true><<<grid, 256, smem, st>>>(q, xmap);
+    else edge_wgrad_tma_kernel<1, false><<<grid, 256, smem, st>>>(q, xmap);
+  } else {
+    if (fused) edge_wgrad_tma_kernel<2, true><<<grid, 256, smem, st>>>(q, xmap);
+    else edge_wgrad_tma_kernel<2, false><<<grid, 256, smem, st>>>(q, xmap);
+  }
   SGK_LAUNCH_CHECK("edge_wgrad_tma_kernel");
   return SGK_OK;
 }

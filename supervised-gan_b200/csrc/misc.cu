@@ -106,13 +106,17 @@ __global__ void axpy_kernel(const float* __restrict__ a, const float* __restrict
 }
 
 // ---------------------------------------------------------------- bias gradient: column sums of [rows, C]
-struct ColGeom { int cols, rlanes, chunks; long long rows_per_chunk; };
+// column sums of x[rows][C]: `cols` column VECTORS (float4 when C % 4 == 0) x `rlanes` row lanes per block, row chunks over
+// blockIdx.x; 4 rows in flight per thread (the reduction is HBM-bound: bytes in flight are what matters)
+struct ColGeom { int V, cols, rlanes, chunks; long long rows_per_chunk; };
 static ColGeom col_geom(size_t rows, int C) {
   ColGeom g;
+  g.V = (C % 4 == 0) ? 4 : 1;
+  const int CV = C / g.V;
   g.cols = 1;
-  while (g.cols * 2 <= C && g.cols < 64) g.cols *= 2;
+  while (g.cols * 2 <= CV && g.cols < 64) g.cols *= 2;
   g.rlanes = 256 / g.cols;
-  long long colgroups = ceil_div(C, g.cols);
+  long long colgroups = ceil_div(CV, g.cols);
   long long chunks = ceil_div64(4LL * sm_count(), colgroups);
   long long maxc = ceil_div64((long long)rows, 4LL * g.rlanes);
   if (chunks > maxc) chunks = maxc;
@@ -122,24 +126,53 @@ static ColGeom col_geom(size_t rows, int C) {
   g.chunks = (int)ceil_div64((long long)rows, g.rows_per_chunk);
   return g;
 }
+template <int V>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int C,
                                                              int cols, int rlanes, long long rows,
                                                              long long rows_per_chunk) {
-  __shared__ float sm[256];
+  __shared__ float sm[256 * V];
+  const int CV = C / V;
   const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
-  const int c = blockIdx.y * cols + tc;
-  float s = 0.f;
-  if (c < C) {
+  const int cv = blockIdx.y * cols + tc;
+  float s[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = 0.f;
+  if (cv < CV) {
     long long r0 = (long long)blockIdx.x * rows_per_chunk, r1 = r0 + rows_per_chunk;
     if (r1 > rows) r1 = rows;
-    for (long long r = r0 + tr; r < r1; r += rlanes) s += __ldg(x + r * C + c);
+    const float* __restrict__ xc = x + cv * V;
+    long long r = r0 + tr;
+    if constexpr (V == 4) {
+      for (; r + 3LL * rlanes < r1; r += 4LL * rlanes) {
+        float4 v0 = __ldg(reinterpret_cast<const float4*>(xc + r * C));
+        float4 v1 = __ldg(reinterpret_cast<const float4*>(xc + (r + rlanes) * C));
+        float4 v2 = __ldg(reinterpret_cast<const float4*>(xc + (r + 2LL * rlanes) * C));
+        float4 v3 = __ldg(reinterpret_cast<const float4*>(xc + (r + 3LL * rlanes) * C));
+        s[0] += (v0.x + v1.x) + (v2.x + v3.x);
+        s[1] += (v0.y + v1.y) + (v2.y + v3.y);
+        s[2] += (v0.z + v1.z) + (v2.z + v3.z);
+        s[3] += (v0.w + v1.w) + (v2.w + v3.w);
+      }
+      for (; r < r1; r += rlanes) {
+        float4 v0 = __ldg(reinterpret_cast<const float4*>(xc + r * C));
+        s[0] += v0.x; s[1] += v0.y; s[2] += v0.z; s[3] += v0.w;
+      }
+    } else {
+      for (; r + 3LL * rlanes < r1; r += 4LL * rlanes)
+        s[0] += (__ldg(xc + r * C) + __ldg(xc + (r + rlanes) * C)) + (__ldg(xc + (r + 2LL * rlanes) * C) + __ldg(xc + (r + 3LL * rlanes) * C));
+      for (; r < r1; r += rlanes) s[0] += __ldg(xc + r * C);
+    }
   }
-  sm[threadIdx.x] = s;
+#pragma unroll
+  for (int i = 0; i < V; ++i) sm[threadIdx.x * V + i] = s[i];
   __syncthreads();
-  if (tr == 0 && c < C) {
-    float a = 0.f;
-    for (int l = 0; l < rlanes; ++l) a += sm[l * cols + tc];
-    part[(long long)blockIdx.x * C + c] = a;
+  if (tr == 0 && cv < CV) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float a = 0.f;
+      for (int l = 0; l < rlanes; ++l) a += sm[(l * cols + tc) * V + i];
+      part[(long long)blockIdx.x * C + cv * V + i] = a;
+    }
   }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int C, int chunks) {
@@ -263,9 +296,24 @@ extern "C" int sgk_bias_grad(const float* dy, float* db, size_t rows, int C, voi
   ColGeom g = col_geom(rows, C);
   size_t need = (size_t)g.chunks * C * sizeof(float);
   if (need > workspace_bytes) { set_error("sgk_bias_grad: workspace %zu < %zu", workspace_bytes, need); return SGK_EWORKSPACE; }
-  dim3 grid((unsigned)g.chunks, (unsigned)ceil_div(C, g.cols));
-  colsum_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, (float*)workspace, C, g.cols, g.rlanes, (long long)rows,
-                                                                g.rows_per_chunk);
+  dim3 grid((unsigned)g.chunks, (unsigned)ceil_div(C / g.V, g.cols));
+  const bool vec = g.V == 4 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0;
+  if (vec)
+    colsum_partial_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, (float*)workspace, C, g.cols, g.rlanes, (long long)rows,
+                                                                     g.rows_per_chunk);
+  else if (g.V == 1)
+    colsum_partial_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, (float*)workspace, C, g.cols, g.rlanes, (long long)rows,
+                                                                     g.rows_per_chunk);
+  else {
+    // unaligned base with C % 4 == 0: scalar geometry
+    ColGeom g1 = g;
+    g1.V = 1; g1.cols = 1;
+    while (g1.cols * 2 <= C && g1.cols < 64) g1.cols *= 2;
+    g1.rlanes = 256 / g1.cols;
+    dim3 grid1((unsigned)g.chunks, (unsigned)ceil_div(C, g1.cols));
+    colsum_partial_kernel<1><<<grid1, 256, 0, (cudaStream_t)stream>>>(dy, (float*)workspace, C, g1.cols, g1.rlanes, (long long)rows,
+                                                                      g.rows_per_chunk);
+  }
   SGK_LAUNCH_CHECK("colsum_partial_kernel");
   colsum_final_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>((const float*)workspace, db, C, g.chunks);
   SGK_LAUNCH_CHECK("colsum_final_kernel");
