@@ -242,7 +242,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te)
-    h2d = B * 3 * 512 * 512 * 4   # the whole 3-channel pinned batch crosses PCIe; 2 channels are selected on the device
+    h2d = int(getattr(m, "h2d_bytes", B * 3 * 512 * 512 * 4))   # counted by set_input from the tensors it copies
     if rank == 0 and os.environ.get("SGK_BENCH_DIAG"):
         def tloop(fn, n=10):
             torch.cuda.synchronize(); t0 = time.perf_counter()

@@ -103,9 +103,26 @@ class FCGANModel(object):
     def set_input(self, input):
         AorB = self.opt.which_direction == 'A'
         src = input['A' if AorB else 'B']
+        idx = self.chnl_idx_input.tolist()
+        if (not src.is_cuda) and src.is_pinned() and src.is_contiguous() and idx == list(range(idx[0], idx[0] + len(idx))):
+            # the selected channels are a contiguous run (e.g. 'rg' of an RGB batch): copy ONLY those planes, one contiguous
+            # asynchronous H2D transfer per sample straight into the (captured) input buffer -- 2/3 of the PCIe bytes of the
+            # whole-batch path and no device-side select
+            shape = (src.shape[0], len(idx)) + tuple(src.shape[2:])
+            if self.input.shape != shape:
+                if self._graph is not None:
+                    raise RuntimeError("cuda_graph: the batch shape is frozen after capture (got %s, captured %s)"
+                                       % (shape, tuple(self.input.shape)))
+                self.input = torch.empty(shape, device=self.device)
+            for n in range(src.shape[0]):
+                self.input[n].copy_(src[n, idx[0]:idx[0] + len(idx)], non_blocking=True)
+            self.h2d_bytes = self.input.numel() * 4
+            self.image_paths = input['A_paths' if AorB else 'B_paths']
+            return
         if src.is_cuda or src.is_pinned():
             # one asynchronous H2D copy of the whole batch, channel selection on the device (the reference selects on the
             # host into pageable memory, fcgan_model.py:118-122)
+            self.h2d_bytes = 0 if src.is_cuda else src.numel() * 4
             if self._stage is None or self._stage.shape != src.shape:
                 self._stage = torch.empty(src.shape, device=self.device)
                 self._idx_dev = self.chnl_idx_input.to(self.device)

@@ -214,3 +214,20 @@ def test_cuda_graph_mode_replays_the_whole_step(S):
     assert m_g.optimizer_G.step_count() == 6
     with pytest.raises(RuntimeError):
         m_g.set_input({"A": torch.zeros(3, 3, 128, 128), "A_paths": ["x"]})
+
+
+def test_set_input_paths_agree(S):
+    """set_input: pinned batch with a contiguous channel run (per-sample plane copies), pinned batch with a scattered
+    selection (whole batch + device select), pageable batch (host select) and device batch all land the same tensor."""
+    from supervised_gan_b200.fcgan_model import FCGANModel
+    gen = torch.Generator().manual_seed(5)
+    batch = torch.rand(2, 3, 64, 64, generator=gen)
+    for chan, idx in (("rg", [0, 1]), ("gb", [1, 2]), ("rb", [0, 2])):
+        m = FCGANModel(); m.initialize(make_opt(pool_size=0, batchSize=2, fineSize=64, noiseSize=1, ngf=8, ndf=8, which_channel=chan))
+        want = batch[:, idx]
+        for src in (batch.clone().pin_memory(), batch.clone(), batch.cuda()):
+            m.set_input({"A": src, "A_paths": ["x"]})
+            torch.cuda.synchronize()
+            assert torch.equal(m.input.cpu(), want), (chan, src.device, src.is_pinned() if not src.is_cuda else None)
+        m.set_input({"A": batch.clone().pin_memory(), "A_paths": ["x"]})
+        assert m.h2d_bytes == (want.numel() if idx != [0, 2] else batch.numel()) * 4
