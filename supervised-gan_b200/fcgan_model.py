@@ -96,6 +96,7 @@ class FCGANModel(object):
         self._graph = None
         self._side = None
         self._stage = None
+        self._copy_stream, self._copy_event = None, None
         self._eager_steps = 0
         self._graph_warmup = int(getattr(opt, "graph_warmup", 3))
 
@@ -114,8 +115,14 @@ class FCGANModel(object):
                     raise RuntimeError("cuda_graph: the batch shape is frozen after capture (got %s, captured %s)"
                                        % (shape, tuple(self.input.shape)))
                 self.input = torch.empty(shape, device=self.device)
-            for n in range(src.shape[0]):
-                self.input[n].copy_(src[n, idx[0]:idx[0] + len(idx)], non_blocking=True)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
+            cs = self._copy_stream
+            cs.wait_stream(torch.cuda.current_stream())      # the previous step's readers of the buffer are done first
+            with torch.cuda.stream(cs):
+                for n in range(src.shape[0]):
+                    self.input[n].copy_(src[n, idx[0]:idx[0] + len(idx)], non_blocking=True)
+                self._copy_event = cs.record_event()
             self.h2d_bytes = self.input.numel() * 4
             self.image_paths = input['A_paths' if AorB else 'B_paths']
             return
@@ -201,19 +208,34 @@ class FCGANModel(object):
                 for p in self.params_D:
                     p.requires_grad_(True)
 
+    def _wait_input(self):
+        """The batch of set_input may still be in flight on the copy stream: order the current stream after it."""
+        if self._copy_event is not None:
+            torch.cuda.current_stream().wait_event(self._copy_event)
+            self._copy_event = None
+
+    def _replay(self):
+        # two graphs: the generator forward does not read the real batch, so the H2D copy of set_input (on its own stream)
+        # overlaps it; the update phases are ordered after the copy
+        g_fwd, g_upd = self._graph
+        g_fwd.replay()
+        self._wait_input()
+        g_upd.replay()
+        ops.bump_weights_epoch()
+
     def optimize_parameters(self):
         if self._graph is not None:
-            self._graph.replay()
-            ops.bump_weights_epoch()
+            self._replay()
             return
         if self.use_graph and self._eager_steps >= self._graph_warmup:
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._optimize_parameters_eager()
-            self._graph = graph
-            graph.replay()          # capture does not execute: run the step this call stands for
-            ops.bump_weights_epoch()
+            g_fwd, g_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fwd):
+                self.forward()
+            with torch.cuda.graph(g_upd, pool=g_fwd.pool()):
+                self._update_phases()
+            self._graph = (g_fwd, g_upd)
+            self._replay()          # capture does not execute: run the step this call stands for
             return
         self._eager_steps += 1
         if self.use_graph:
@@ -231,6 +253,10 @@ class FCGANModel(object):
 
     def _optimize_parameters_eager(self):
         self.forward()
+        self._wait_input()
+        self._update_phases()
+
+    def _update_phases(self):
         for _ in range(self.opt.n_update_D):
             self.optimizer_D.zero_grad(set_to_none=True)
             if self.grad_sync is not None and hasattr(self.grad_sync, "arm"):
