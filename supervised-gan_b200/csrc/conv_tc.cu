@@ -414,6 +414,8 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
     const int r_own = warp * 32 + lane;
     const uint32_t stg = smem_base;   // stage 0's A region is idle once the accumulator is complete
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    const bool simple_act = p.act == SGK_ACT_NONE || p.act == SGK_ACT_RELU || p.act == SGK_ACT_LRELU;
+    const float act_sl = p.act == SGK_ACT_NONE ? 1.f : (p.act == SGK_ACT_RELU ? 0.f : p.slope);
     for (int qc = 0; qc < nvalid * p.BN; qc += 32) {
       const int q = qc >= p.BN ? 1 : 0;
       const int cc = qc - q * p.BN;
@@ -421,20 +423,16 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
       uint32_t v[32];
       tmem_ld32(lane_addr + (uint32_t)qc, v);
       tmem_ld_wait();
+      // raw accumulators through the smem transpose; bias + activation afterwards, on the 4 consecutive channels each
+      // thread then owns (ReLU / LeakyReLU / identity share the branch-free form x > 0 ? x : x * s)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cc + 4 * q));
-        const float o0 = act_apply(__uint_as_float(v[4 * q + 0]) + bv.x, p.act, p.slope);
-        const float o1 = act_apply(__uint_as_float(v[4 * q + 1]) + bv.y, p.act, p.slope);
-        const float o2 = act_apply(__uint_as_float(v[4 * q + 2]) + bv.z, p.act, p.slope);
-        const float o3 = act_apply(__uint_as_float(v[4 * q + 3]) + bv.w, p.act, p.slope);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r_own * 128u +
-                                                                    (((uint32_t)q ^ (uint32_t)(r_own & 7)) << 4)),
-                     "f"(o0), "f"(o1), "f"(o2), "f"(o3)
+      for (int q8 = 0; q8 < 8; ++q8)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)r_own * 128u +
+                                                                    (((uint32_t)q8 ^ (uint32_t)(r_own & 7)) << 4)),
+                     "r"(v[4 * q8]), "r"(v[4 * q8 + 1]), "r"(v[4 * q8 + 2]), "r"(v[4 * q8 + 3])
                      : "memory");
-      }
       __syncwarp();
+      const float4 b4 = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cc + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = warp * 32 + i * 4 + rsub;
@@ -444,6 +442,14 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
                      : "r"(stg + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
+        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+        if (simple_act) {
+          o.x = o.x > 0.f ? o.x : o.x * act_sl; o.y = o.y > 0.f ? o.y : o.y * act_sl;
+          o.z = o.z > 0.f ? o.z : o.z * act_sl; o.w = o.w > 0.f ? o.w : o.w * act_sl;
+        } else {
+          o.x = act_apply(o.x, p.act, p.slope); o.y = act_apply(o.y, p.act, p.slope);
+          o.z = act_apply(o.z, p.act, p.slope); o.w = act_apply(o.w, p.act, p.slope);
+        }
         if (ry < p.th && oy < P.Hp && ox < P.Wp) {
           float* dstp = p.out + (((long long)n * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co + n0 + cc + 4 * j;
           *reinterpret_cast<float4*>(dstp) = o;
@@ -792,6 +798,201 @@ static EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+// ================================================================================================
+// Persistent "window" kernel for the 2-channel image layers (k4 s2, K = 32): NO im2col at all.  In the NO-SWIZZLE K-major
+// operand layout a core matrix is 8 rows x 16 B at a 16-B row pitch -- exactly how the patches of 8 neighbouring output
+// pixels overlap in a raw 2-channel image row (pixel stride = s*Cg floats = 16 B).  So the A descriptor of tap row a points
+// INTO the raw patch: start = patch + a*row_pitch, LBO (next K chunk) = 16 B = the same window one pixel further,
+// SBO (next 8 rows = next output row of the 8 x 16 tile) = s*row_pitch (tools/umma_window_test.cu).  A tile needs one
+// 3-D TMA box of 34 rows x 144 B (4.9 KB, zero-filled out of bounds = the conv padding) instead of a 16 KB im2col image made
+// of 512 32-byte pieces, which is what bounded the im2col variant (TMA request rate).  The CTA is persistent: weights and
+// tensor memory are set up once; warp 0 streams patches through a ring, warp 1 issues the 4 MMAs of a tile into one of TWO
+// accumulators, warps 4-7 drain the other one (bias + activation, smem transpose, coalesced NHWC stores).
+// ================================================================================================
+constexpr int IP_THREADS = 256;
+constexpr int WN_TW = 8, WN_TH = 16;              // output tile: m = oy*8 + ox
+struct ImPParams {
+  const float* bias;
+  float* out;
+  int N, Ho, Wo, Co;
+  int act;
+  float slope;
+  int tiles_x, tiles_y;
+  long long total;      // N * tiles_x * tiles_y
+  int BN, stages, tmem_cols;
+  int s, off, Cg;       // conv stride, -pad, input channels
+  uint32_t row_bytes, patch_rows, stage_stride;
+  int nacc;             // TMEM accumulators in flight (nacc * BN columns)
+  int dbg;              // experiments: 1 = no global stores, 2 = no MMAs, 4 = no patch loads
+};
+struct alignas(64) ImPMaps {
+  CUtensorMap w;  // packed weights [Co][32], box {32, BN}, SWIZZLE_128B
+  CUtensorMap a;  // raw image {W*Cg, H, N}, box {row floats, patch rows, 1}, no swizzle
+};
+
+__device__ __forceinline__ uint64_t make_noswz_kmajor_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // next 16-B K chunk
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // next 8-row group
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100); layout type 0 = no swizzle
+  return d;
+}
+
+__global__ void __launch_bounds__(IP_THREADS, 2)
+conv_window_persist_kernel(const __grid_constant__ ImPParams p, const __grid_constant__ ImPMaps maps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t w_base = smem_base + (((uint32_t)S * p.stage_stride + 1023u) & ~1023u);   // weights: BN x 128 B, loaded once
+  const uint32_t stg_base = w_base + (((uint32_t)p.BN * 128u + 1023u) & ~1023u);            // epilogue transpose: 128 x 128 B
+  const uint32_t bar_base = stg_base + TC_A_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
+  const int NA = p.nacc;   // accumulators in flight: the mbarrier hand-offs between the roles cost ~1 us each, so the
+                           // tile rate is NA tiles per round trip (2 accumulators measured 4 us per tile)
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * S + NA + a); };
+  const uint32_t w_bar = bar_base + 8u * (uint32_t)(2 * S + 2 * NA);
+  const uint32_t tmem_slot = w_bar + 8u;
+  const int n0 = blockIdx.y * p.BN;
+  const int per_img = p.tiles_x * p.tiles_y;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < NA; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);   // one arrival per epilogue warp
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_acc;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // =============================================================== TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, (uint32_t)p.BN * 128u);
+      tma_load_2d(w_base, &maps.w, 0, n0, w_bar);
+      const uint32_t patch_bytes = p.row_bytes * p.patch_rows;
+      int it = 0;
+      for (long long t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
+        const int s = it % S;
+        mbar_wait(empty_bar(s), (uint32_t)(((it / S) & 1) ^ 1));
+        const int n = (int)(t / per_img);
+        const int r2 = (int)(t - (long long)n * per_img);
+        const int ty0 = (r2 / p.tiles_x) * WN_TH, tx0 = (r2 % p.tiles_x) * WN_TW;
+        if (p.dbg & 4) { mbar_arrive(full_bar(s)); continue; }
+        mbar_arrive_expect_tx(full_bar(s), patch_bytes);
+        tma_load_3d(smem_base + (uint32_t)s * p.stage_stride, &maps.a, (tx0 * p.s + p.off) * p.Cg, ty0 * p.s + p.off, n, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN);
+      mbar_wait(w_bar, 0);
+      int it = 0;
+      for (long long t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
+        const int s = it % S, acc = it % NA;
+        mbar_wait(tempty_bar(acc), (uint32_t)(((it / NA) & 1) ^ 1));   // the epilogue has drained this accumulator
+        mbar_wait(full_bar(s), (uint32_t)((it / S) & 1));
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)s * p.stage_stride;
+#pragma unroll
+        for (int kk = 0; kk < ((p.dbg & 2) ? 1 : 4); ++kk)   // tap row kk: windows of the raw patch
+          umma_tf32(tmem_acc + (uint32_t)(acc * p.BN), make_noswz_kmajor_desc(a_addr + kk * p.row_bytes, 16u, (uint32_t)p.s * p.row_bytes),
+                    make_sw128_kmajor_desc(w_base + kk * 32), idesc, (uint32_t)(kk != 0));
+        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================================================== epilogue (warp w owns TMEM lanes 32*(w-4)...)
+    // Per tile and 32-column chunk: tcgen05.ld -> raw accumulators transposed through shared memory -> every thread then owns
+    // 4 consecutive channels of 8 pixels: bias (held in registers for the CTA's lifetime) + activation + one 16-B store each.
+    // ReLU / LeakyReLU / identity share the branch-free form x > 0 ? x : x * s.
+    const int ew = warp - 4;
+    const uint32_t j = (uint32_t)(lane & 7);
+    const int rsub = lane >> 3;
+    const int r_own = ew * 32 + lane;
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)(ew * 32) << 16);
+    const bool simple = p.act == SGK_ACT_NONE || p.act == SGK_ACT_RELU || p.act == SGK_ACT_LRELU;
+    const float sl = p.act == SGK_ACT_NONE ? 1.f : (p.act == SGK_ACT_RELU ? 0.f : p.slope);
+    float4 bias4[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      bias4[c] = (p.bias != nullptr && c * 32 < p.BN) ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + 4 * j))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    int it = 0;
+    long long t = blockIdx.x;
+    int n = (int)(t / per_img);
+    int r2 = (int)(t - (long long)n * per_img);
+    for (; t < p.total; t += gridDim.x, ++it) {
+      const int acc = it % NA;
+      const int ty0 = (r2 / p.tiles_x) * WN_TH, tx0 = (r2 % p.tiles_x) * WN_TW;
+      mbar_wait(tfull_bar(acc), (uint32_t)((it / NA) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < p.BN; cc += 32) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + (uint32_t)(acc * p.BN + cc), v);
+        tmem_ld_wait();
+        if (cc + 32 >= p.BN) {
+          // the whole accumulator is in registers: hand it back to the MMA warp before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (p.dbg & 8) continue;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_base + (uint32_t)r_own * 128u +
+                                                                      (((uint32_t)q ^ (uint32_t)(r_own & 7)) << 4)),
+                       "r"(v[4 * q]), "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                       : "memory");
+        __syncwarp();
+        const float4 b4 = bias4[cc >> 5];
+        float* __restrict__ obase = p.out + (long long)n * p.Ho * p.Wo * p.Co + n0 + cc + 4 * j;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = ew * 32 + i * 4 + rsub;
+          const int oy = ty0 + (r >> 3), ox = tx0 + (r & 7);
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "r"(stg_base + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
+          o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+          if (simple) {
+            o.x = o.x > 0.f ? o.x : o.x * sl; o.y = o.y > 0.f ? o.y : o.y * sl;
+            o.z = o.z > 0.f ? o.z : o.z * sl; o.w = o.w > 0.f ? o.w : o.w * sl;
+          } else {
+            o.x = act_apply(o.x, p.act, p.slope); o.y = act_apply(o.y, p.act, p.slope);
+            o.z = act_apply(o.z, p.act, p.slope); o.w = act_apply(o.w, p.act, p.slope);
+          }
+          if (oy < p.Ho && ox < p.Wo && !(p.dbg & 1)) *reinterpret_cast<float4*>(obase + ((long long)oy * p.Wo + ox) * p.Co) = o;
+        }
+        __syncwarp();
+      }
+      // next tile of this CTA: advance (n, r2) without 64-bit divisions
+      r2 += (int)gridDim.x;
+      while (r2 >= per_img) { r2 -= per_img; ++n; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+}
+
 static int pick_bn(int Co) {
   for (int bn : {256, 128, 64, 32})
     if (Co % bn == 0) return bn;
@@ -809,7 +1010,8 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   const bool im2col = use_im2col && g.transposed_type == 0 && g.nphase == 1 && g.k == 4 && g.ph[0].is == 2 && g.ph[0].ioy == 0 &&
                       g.ph[0].iox == 0 && g.Cg == 2 && (g.Co % 32) == 0 && (g.Wi % 2) == 0 && g.ph[0].kstride == 32 &&
                       (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-  if (!im2col && !tc_thin && ((g.Cg % 32) != 0 || (g.Co % 32) != 0)) return SGK_EUNSUPPORTED;
+  const bool window_shape = g.transposed_type == 0 && g.nphase == 1 && g.k == 4 && g.ph[0].is == 2 && g.Cg == 2 && (g.Co % 32) == 0;
+  if (!im2col && !window_shape && !tc_thin && ((g.Cg % 32) != 0 || (g.Co % 32) != 0)) return SGK_EUNSUPPORTED;
   // N tile: a divisor of Cout in {256,128,64,32}, or one 16-wide tile for thin outputs (Cout <= 16: images, logits)
   int BN = pick_bn(g.Co);
   if (BN == 0) {
@@ -875,6 +1077,57 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
   // step); it stays available for experiments with SGK_TC_PERSIST=1.
   // ---- TMA-fed variant: activations as 4-D tensor boxes (needs 32-channel chunks and full 32-column N tiles)
   static const bool use_tma = !(getenv("SGK_TC_TMA") != nullptr && atoi(getenv("SGK_TC_TMA")) == 0);
+  // window mode (persistent, raw patches): direct conv k4 s2 on a 2-channel image whose padding offset is 16-B aligned
+  static const bool window_on = !(getenv("SGK_TC_WINDOW") != nullptr && atoi(getenv("SGK_TC_WINDOW")) == 0);
+  const bool window = window_on && g.transposed_type == 0 && g.nphase == 1 && g.k == 4 && g.ph[0].is == 2 && g.Cg == 2 &&
+                      (g.Co % 32) == 0 && g.ph[0].kstride == 32 && g.ph[0].ioy == g.ph[0].iox && g.ph[0].ioy <= 0 &&
+                      ((-g.ph[0].ioy) * g.Cg * 4) % 16 == 0 && ((long long)g.Wi * g.Cg * 4) % 16 == 0 &&
+                      (reinterpret_cast<uintptr_t>(in) & 15) == 0 && BN <= 128;
+  if (window) {
+    const int is = g.ph[0].is;
+    ImPParams q{};
+    ImPMaps tm{};
+    q.bias = bias; q.out = out; q.N = g.N; q.Ho = g.Ho; q.Wo = g.Wo; q.Co = g.Co; q.act = act; q.slope = slope;
+    q.tiles_x = ceil_div(g.Wo, WN_TW); q.tiles_y = ceil_div(g.Ho, WN_TH);
+    q.total = (long long)g.N * q.tiles_x * q.tiles_y;
+    q.BN = BN; q.stages = 8;
+    q.nacc = 256 / BN < 8 ? 256 / BN : 8;
+    { const char* ev = getenv("SGK_WINDOW_NACC"); if (ev && atoi(ev) >= 1 && atoi(ev) * BN <= 256) q.nacc = atoi(ev); }
+    const int wcols = q.nacc * BN;
+    q.tmem_cols = wcols <= 32 ? 32 : (wcols <= 64 ? 64 : (wcols <= 128 ? 128 : 256));
+    q.s = is; q.off = g.ph[0].ioy; q.Cg = g.Cg;
+    q.dbg = getenv("SGK_WINDOW_DBG") ? atoi(getenv("SGK_WINDOW_DBG")) : 0;
+    const uint32_t row_floats = (uint32_t)(((WN_TW - 1) * is + 4) * g.Cg);
+    q.row_bytes = row_floats * 4u;
+    q.patch_rows = (uint32_t)((WN_TH - 1) * is + 4);
+    q.stage_stride = (q.row_bytes * q.patch_rows + 127u) & ~127u;
+    tm.w = maps.w[0];
+    cuuint64_t idim[3] = {(cuuint64_t)g.Wi * g.Cg, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+    cuuint64_t istr[2] = {(cuuint64_t)g.Wi * g.Cg * 4, (cuuint64_t)g.Hi * g.Wi * g.Cg * 4};
+    cuuint32_t ibox[3] = {row_floats, q.patch_rows, 1u};
+    cuuint32_t iest[3] = {1u, 1u, 1u};
+    CUresult r = encode(&tm.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)in, idim, istr, ibox, iest, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(window) failed (%d)", (int)r); return SGK_ECUDA; }
+    const size_t ismem = (((size_t)q.stages * q.stage_stride + 1023) & ~(size_t)1023) + (((size_t)BN * 128 + 1023) & ~(size_t)1023) +
+                         TC_A_BYTES + 8 * (2 * q.stages + 2 * q.nacc + 4) + 1024;
+    static bool iattr = false;
+    if (!iattr) {
+      cudaError_t e = cudaFuncSetAttribute(conv_window_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_window_persist_kernel)");
+      iattr = true;
+    }
+    int per_sm = 2;
+    { const char* ev = getenv("SGK_WINDOW_CTAS"); if (ev && atoi(ev) >= 1) per_sm = atoi(ev); }
+    if (per_sm * q.tmem_cols > 512) per_sm = 512 / q.tmem_cols;
+    long long gx = (long long)per_sm * sm_count() / (g.Co / BN);
+    if (gx < 1) gx = 1;
+    if (gx > q.total) gx = q.total;
+    dim3 igrid((unsigned)gx, (unsigned)(g.Co / BN));
+    conv_window_persist_kernel<<<igrid, IP_THREADS, ismem, st>>>(q, tm);
+    SGK_LAUNCH_CHECK("conv_window_persist_kernel");
+    return SGK_OK;
+  }
   if (im2col || (use_tma && cs == 0 && BN >= 32)) {
     const int is = g.ph[0].is;
     TmaParams q{};
@@ -1528,11 +1781,6 @@ static WTcPlan wgrad_tc_plan(const EquivConv& e) {
 // ================================================================================================
 constexpr int EW_TH = 8, EW_TW = 32, EW_K = 32;
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-               : "memory");
-}
 
 struct EdgeWParams {
   const float* g;

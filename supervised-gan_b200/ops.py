@@ -236,10 +236,15 @@ class _ConvFn(torch.autograd.Function):
         elif cfg.padded_image_layer(w, x.shape):
             st = _stream()
             pd = desc.pad
-            xp = torch.empty((desc.N, desc.Hin + 2 * pd, desc.Win + 2 * pd, desc.Cin), dtype=torch.float32, device=x.device)
-            L.check(lib.sgk_pad_nhwc(_p(x), _p(xp), desc.N, desc.Hin, desc.Win, desc.Cin, pd, st), "pad_nhwc")
-            descp = L.SgkConvDesc(desc.N, desc.Cin, desc.Hin + 2 * pd, desc.Win + 2 * pd, desc.Cout, desc.Hout, desc.Wout,
-                                  desc.k, desc.stride, 0, 0, desc.precision)
+            if (pd * desc.Cin * 4) % 16 == 0:
+                # the padding offset is 16-B aligned: the TMA boxes of the window kernel / edge weight gradient start inside
+                # the raw tensor and their out-of-bounds zero fill IS the padding -- no padded copy
+                xp, descp = x, desc
+            else:
+                xp = torch.empty((desc.N, desc.Hin + 2 * pd, desc.Win + 2 * pd, desc.Cin), dtype=torch.float32, device=x.device)
+                L.check(lib.sgk_pad_nhwc(_p(x), _p(xp), desc.N, desc.Hin, desc.Win, desc.Cin, pd, st), "pad_nhwc")
+                descp = L.SgkConvDesc(desc.N, desc.Cin, desc.Hin + 2 * pd, desc.Win + 2 * pd, desc.Cout, desc.Hout, desc.Wout,
+                                      desc.k, desc.stride, 0, 0, desc.precision)
             wp = cfg.packed(weight, desc, L.OP_FWD)      # the packed layout does not depend on the padding
             L.check(_timed(_conv_tag("fwd", descp), _conv_flops(descp), lambda: lib.sgk_conv_fwd(
                 ctypes.byref(descp), _p(xp), _p(wp), _p(b), _p(y), act, slope, st)), "conv_fwd(padded)")
