@@ -444,8 +444,8 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
                      : "r"(stg + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
         o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
         if (simple_act) {
-          o.x = o.x > 0.f ? o.x : o.x * act_sl; o.y = o.y > 0.f ? o.y : o.y * act_sl;
-          o.z = o.z > 0.f ? o.z : o.z * act_sl; o.w = o.w > 0.f ? o.w : o.w * act_sl;
+          o.x = act_relu_family(o.x, act_sl); o.y = act_relu_family(o.y, act_sl);
+          o.z = act_relu_family(o.z, act_sl); o.w = act_relu_family(o.w, act_sl);
         } else {
           o.x = act_apply(o.x, p.act, p.slope); o.y = act_apply(o.y, p.act, p.slope);
           o.z = act_apply(o.z, p.act, p.slope); o.w = act_apply(o.w, p.act, p.slope);
@@ -973,8 +973,8 @@ conv_window_persist_kernel(const __grid_constant__ ImPParams p, const __grid_con
                        : "r"(stg_base + (uint32_t)r * 128u + ((j ^ (uint32_t)(r & 7)) << 4)));
           o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
           if (simple) {
-            o.x = o.x > 0.f ? o.x : o.x * sl; o.y = o.y > 0.f ? o.y : o.y * sl;
-            o.z = o.z > 0.f ? o.z : o.z * sl; o.w = o.w > 0.f ? o.w : o.w * sl;
+            o.x = act_relu_family(o.x, sl); o.y = act_relu_family(o.y, sl);
+            o.z = act_relu_family(o.z, sl); o.w = act_relu_family(o.w, sl);
           } else {
             o.x = act_apply(o.x, p.act, p.slope); o.y = act_apply(o.y, p.act, p.slope);
             o.z = act_apply(o.z, p.act, p.slope); o.w = act_apply(o.w, p.act, p.slope);
