@@ -91,6 +91,16 @@ size_t sgk_conv_packed_weight_elems(const SgkConvDesc* d, int op);
 /* w_raw: reference-layout parameter; w_packed: K-major operand for `op`.  Called once per
  * optimiser step per layer (weights only change in Adam). */
 int sgk_conv_pack_weight(const SgkConvDesc* d, int op, const float* w_raw, float* w_packed, void* stream);
+/* The same for several layers in one launch per 8 jobs (after an optimiser step all packed copies of the updated weights
+ * are refreshed together; replaces the implicit weight re-layout cuDNN does inside every nn.Conv2d call). */
+typedef struct SgkPackJob {
+  SgkConvDesc desc;
+  int32_t op;        /* SGK_OP_FWD or SGK_OP_DGRAD */
+  int32_t reserved;
+  const float* w_raw;
+  float* w_packed;
+} SgkPackJob;
+int sgk_conv_pack_weight_multi(const SgkPackJob* jobs, int n, void* stream);
 
 /* y = act(conv(x) + bias).  x, y NHWC.  bias may be NULL.  act: enum SgkAct (slope for LRELU). */
 int sgk_conv_fwd(const SgkConvDesc* d, const float* x, const float* w_packed_fwd, const float* bias,

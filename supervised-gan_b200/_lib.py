@@ -28,6 +28,12 @@ class SgkAdamTensor(Structure):
 
 # name -> (restype, argtypes); every symbol include/sgk.h declares
 P = c_void_p
+class SgkPackJob(ctypes.Structure):
+    """include/sgk.h: struct SgkPackJob."""
+    _fields_ = [("desc", SgkConvDesc), ("op", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("w_raw", ctypes.c_void_p), ("w_packed", ctypes.c_void_p)]
+
+
 SIGNATURES = {
     "sgk_version": (c_int, []),
     "sgk_last_error": (c_char_p, []),
@@ -37,6 +43,7 @@ SIGNATURES = {
     "sgk_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "sgk_conv_packed_weight_elems": (c_size_t, [POINTER(SgkConvDesc), c_int]),
     "sgk_conv_pack_weight": (c_int, [POINTER(SgkConvDesc), c_int, P, P, P]),
+    "sgk_conv_pack_weight_multi": (c_int, [POINTER(SgkPackJob), c_int, P]),
     "sgk_conv_fwd": (c_int, [POINTER(SgkConvDesc), P, P, P, P, c_int, c_float, P]),
     "sgk_conv_dgrad": (c_int, [POINTER(SgkConvDesc), P, P, P, P]),
     "sgk_conv_wgrad_workspace_bytes": (c_size_t, [POINTER(SgkConvDesc)]),

@@ -22,8 +22,7 @@ struct PackParams {
   long long total;
 };
 
-__global__ void pack_weight_kernel(const __grid_constant__ PackParams p) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_one(const PackParams& p, long long idx) {
   if (idx >= p.total) return;
   int ph = 0;
 #pragma unroll
@@ -45,6 +44,26 @@ __global__ void pack_weight_kernel(const __grid_constant__ PackParams p) {
   int o = p.transposed_type ? c : n;
   int i = p.transposed_type ? n : c;
   p.packed[idx] = p.raw[(((long long)o * p.I + i) * p.k + ry) * p.k + rx];
+}
+
+__global__ void pack_weight_kernel(const __grid_constant__ PackParams p) {
+  pack_one(p, (long long)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// several layers per launch: after an optimiser step every packed copy of the updated weights is refreshed at once (the
+// per-layer launches are ~4 us each, 33 per step)
+constexpr int PACK_MULTI = 8;
+struct PackMultiParams {
+  PackParams job[PACK_MULTI];
+  int block_begin[PACK_MULTI + 1];
+  int njobs;
+};
+__global__ void pack_weight_multi_kernel(const __grid_constant__ PackMultiParams m) {
+  int j = 0;
+#pragma unroll
+  for (int i = 1; i < PACK_MULTI; ++i)
+    if (i < m.njobs && (int)blockIdx.x >= m.block_begin[i]) j = i;
+  pack_one(m.job[j], (long long)((int)blockIdx.x - m.block_begin[j]) * blockDim.x + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -980,6 +999,45 @@ extern "C" int sgk_conv_pack_weight(const SgkConvDesc* d, int op, const float* w
   pack_weight_kernel<<<(unsigned)ceil_div64(p.total, 256), 256, 0, (cudaStream_t)stream>>>(p);
   SGK_LAUNCH_CHECK("pack_weight_kernel");
   return SGK_OK;
+}
+
+extern "C" int sgk_conv_pack_weight_multi(const SgkPackJob* jobs, int n, void* stream) {
+  SGK_CHECK_ARG(jobs || n == 0, "sgk_conv_pack_weight_multi: null jobs");
+  PackMultiParams m{};
+  int nb = 0;
+  auto flush = [&]() -> int {
+    if (m.njobs == 0) return SGK_OK;
+    m.block_begin[m.njobs] = nb;
+    pack_weight_multi_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(m);
+    SGK_LAUNCH_CHECK("pack_weight_multi_kernel");
+    m.njobs = 0;
+    nb = 0;
+    return SGK_OK;
+  };
+  for (int i = 0; i < n; ++i) {
+    const SgkPackJob& J = jobs[i];
+    SGK_CHECK_ARG(J.w_raw && J.w_packed, "sgk_conv_pack_weight_multi: null pointer in job");
+    int rc = validate_desc(J.desc);
+    if (rc) return rc;
+    if (J.op != SGK_OP_FWD && J.op != SGK_OP_DGRAD) { set_error("sgk_conv_pack_weight_multi: op must be FWD or DGRAD"); return SGK_EINVAL; }
+    GatherPlan g = make_gather_plan(J.desc, J.op);
+    if (g.packed_elems == 0) continue;
+    const long long blocks = ceil_div64(g.packed_elems, 256);
+    if (blocks > 0x3fffffffLL) { set_error("sgk_conv_pack_weight_multi: weight too large"); return SGK_EUNSUPPORTED; }
+    if (m.njobs == PACK_MULTI || (long long)nb + blocks > 0x7fffffffLL) {
+      rc = flush();
+      if (rc) return rc;
+    }
+    PackParams& p = m.job[m.njobs];
+    p = PackParams{};
+    p.raw = J.w_raw; p.packed = J.w_packed; p.O = g.O; p.I = g.I; p.k = g.k;
+    p.transposed_type = g.transposed_type; p.nphase = g.nphase; p.total = g.packed_elems;
+    for (int q = 0; q < g.nphase; ++q) p.ph[q] = g.ph[q];
+    m.block_begin[m.njobs] = nb;
+    nb += (int)blocks;
+    ++m.njobs;
+  }
+  return flush();
 }
 
 namespace sgk {

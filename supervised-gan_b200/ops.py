@@ -6,6 +6,7 @@ with the reference's nn.Modules.  PyTorch is used for device memory (caching all
 and the autograd graph only -- all arithmetic is in the .so; there is no CPU / ATen fallback.
 """
 import ctypes
+import weakref
 import os
 
 import torch
@@ -41,8 +42,55 @@ def bump_weights_epoch(params=None):
         _weights_epoch += 1
         return
     _epoch_counter += 1
+    ptrs = []
     for p in params:
         _param_epoch[p.data_ptr()] = _epoch_counter
+        ptrs.append(p.data_ptr())
+    _repack_registered(ptrs)
+
+
+# (cfg, op) pairs that have packed a given parameter before: their packed copies are refreshed TOGETHER right after the
+# optimiser step that changed the parameter (one multi-job launch per 8 layers instead of one launch per layer and use)
+_pack_registry = {}     # data_ptr -> {(id(cfg), op): (weakref(cfg), weakref(weight), desc)}
+_multi_pack = os.environ.get("SGK_MULTI_PACK", "1") != "0"
+
+
+def _register_pack(cfg, weight, desc, op):
+    ent = _pack_registry.setdefault(weight.data_ptr(), {})
+    key = (id(cfg), op)
+    if key not in ent:
+        d = L.SgkConvDesc()
+        ctypes.pointer(d)[0] = desc
+        ent[key] = (weakref.ref(cfg), weakref.ref(weight), d)
+
+
+def _repack_registered(ptrs):
+    if not _multi_pack:
+        return
+    jobs, done = [], []
+    for ptr in ptrs:
+        ent = _pack_registry.get(ptr)
+        if not ent:
+            continue
+        for key, (cref, wref, desc) in list(ent.items()):
+            cfg, weight = cref(), wref()
+            if cfg is None or weight is None or weight.data_ptr() != ptr:
+                del ent[key]
+                continue
+            op = key[1]
+            cur = cfg._packed.get(op)
+            if cur is None:
+                continue
+            jobs.append((desc, op, weight.data_ptr(), cur[1].data_ptr()))
+            done.append((cfg, op, weight, cur[1]))
+    if not jobs:
+        return
+    arr = (L.SgkPackJob * len(jobs))()
+    for i, (desc, op, wptr, optr) in enumerate(jobs):
+        arr[i].desc, arr[i].op, arr[i].w_raw, arr[i].w_packed = desc, op, wptr, optr
+    L.check(L.load().sgk_conv_pack_weight_multi(arr, len(jobs), _stream()), "conv_pack_weight_multi")
+    for cfg, op, weight, buf in done:
+        cfg._packed[op] = (_weight_tag(weight), buf)
 
 
 def _weight_tag(weight):
@@ -165,6 +213,7 @@ class ConvCfg:
             torch.empty(n, dtype=torch.float32, device=weight.device)
         L.check(lib.sgk_conv_pack_weight(ctypes.byref(desc), op, _p(weight), _p(buf), _stream()), "conv_pack_weight")
         self._packed[op] = (tag, buf)
+        _register_pack(self, weight, desc, op)
         return buf
 
     # ---- image layers (2-channel input, k4 s2) on the tensor-core path: convolve a zero-padded copy with pad=0 so that one

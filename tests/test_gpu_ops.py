@@ -371,3 +371,36 @@ def test_tap_fold_unfold_and_pad(S):
         np.testing.assert_array_equal(xp.cpu().numpy(), np.pad(x, ((0, 0), (p, p), (p, p), (0, 0))))
     # rows beyond 32 are refused
     assert lib.sgk_tap_fold_fwd(y.data_ptr(), None, y.data_ptr(), 1, 4, 4, 3, 4, 2, 0, 0.0, st) != 0
+
+
+def test_pack_weight_multi_matches_single(S):
+    """sgk_conv_pack_weight_multi (8 jobs per launch) writes exactly what the per-layer call writes, for direct and
+    transposed layers, forward and dgrad layouts, across a launch boundary (11 jobs)."""
+    import ctypes
+    L = S._lib
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(7)
+    shapes = [(0, 32, 64, 4, 2, 2), (0, 128, 256, 4, 1, 2), (1, 64, 32, 4, 2, 1), (0, 2, 32, 4, 2, 2), (1, 32, 2, 4, 2, 1),
+              (0, 5, 7, 3, 1, 1)]
+    jobs, singles = [], []
+    for (tr, ci, co, k, s, p) in shapes:
+        H = 16
+        Ho = (H - 1) * s - 2 * p + k if tr else (H + 2 * p - k) // s + 1
+        d = L.SgkConvDesc(1, ci, H, H, co, Ho, Ho, k, s, p, tr, 0)
+        w = torch.tensor(rng.standard_normal((ci, co, k, k) if tr else (co, ci, k, k)), dtype=torch.float32, device="cuda")
+        for op in (L.OP_FWD, L.OP_DGRAD):
+            n = lib.sgk_conv_packed_weight_elems(ctypes.byref(d), op)
+            a = torch.full((n,), -7.0, device="cuda"); b = torch.full((n,), -9.0, device="cuda")
+            assert lib.sgk_conv_pack_weight(ctypes.byref(d), op, w.data_ptr(), a.data_ptr(), st) == 0
+            jobs.append((d, op, w, b)); singles.append(a)
+    jobs, singles = jobs[:11], singles[:11]
+    arr = (L.SgkPackJob * len(jobs))()
+    for i, (d, op, w, b) in enumerate(jobs):
+        arr[i].desc, arr[i].op, arr[i].w_raw, arr[i].w_packed = d, op, w.data_ptr(), b.data_ptr()
+    n0 = lib.sgk_launch_count()
+    assert lib.sgk_conv_pack_weight_multi(arr, len(jobs), st) == 0
+    assert lib.sgk_launch_count() - n0 == 2          # 8 + 3 jobs
+    torch.cuda.synchronize()
+    for (d, op, w, b), a in zip(jobs, singles):
+        assert torch.equal(a, b)
