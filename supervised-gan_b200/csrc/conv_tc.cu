@@ -1,7 +1,19 @@
-// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (SGK_TF32): the gather GEMM of conv_plan.h
-//   out[128 pixels x BN channels] += A[128 x 32] * B[BN x 32]^T      per k-block (one tap, 32 channels)
-// with fp32 storage, kind::tf32 tensor-core math and fp32 accumulation in tensor memory.
+// tcgen05 / TMEM implicit-GEMM convolutions for sm_100a (SGK_TF32): the gather GEMM and the pixel reduction of conv_plan.h
+// with fp32 storage, kind::tf32 tensor-core math and fp32 accumulation in tensor memory.  Kernels in this file:
 //
+//   conv_tma_tc_kernel          fwd / dgrad of every layer with 32-channel chunks: one CTA = one (or two) 128-pixel M tiles x
+//                               one BN-channel N tile; lane 0 of warp 4 feeds BOTH operands by TMA (activations as 4-D boxes of
+//                               the NHWC tensor: traversal stride = conv stride, out-of-bounds zero fill = padding), lane 0 of
+//                               warp 5 issues tcgen05.mma, warps 0-3 are the epilogue.  Default path.
+//   conv_window_persist_kernel  2-channel image layers: persistent, the A operand is read straight from raw image patches
+//                               through overlapping no-swizzle descriptors (no im2col).
+//   conv_wgrad_tma_kernel       weight gradient: pixels are the reduction dim, both operands MN-major
+//                               (SWIZZLE_128B_BASE32B), fed by TMA; split over pixel ranges + ordered reduce.
+//   edge_wgrad_tma_kernel       weight gradient of the image layers on the FFMA pipe, TMA-fed patches.
+//   conv_gather_tc_kernel, conv_gather_tc_persist_kernel, conv_wgrad_tc_kernel
+//                               the cp.async-gather predecessors (fallbacks: SGK_TC_TMA=0 / SGK_WTMA=0 / thin shapes).
+//
+// The description below is of conv_gather_tc_kernel, whose roles and epilogue the TMA kernels inherited.
 // CTA = 192 threads, one 128-pixel M tile x one BN-channel N tile, 2 CTAs resident per SM (the prologue /
 // epilogue of one overlaps the main loop of the other):
 //   warps 0-3  A producers.  Tile row r = one output pixel; its (image, y0, x0) is decoded once into a smem table.
