@@ -896,7 +896,17 @@ __global__ void __launch_bounds__(256) wgrad_reduce_vec_kernel(const float* __re
   const long long idx = gid * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (idx < total) {
-    for (int sp = l; sp < splits; sp += RL) {
+    int sp = l;
+    // 4 independent loads in flight per thread (with a few dozen splits a lane otherwise holds 2-3 dependent-latency loads)
+    for (; sp + 3 * RL < splits; sp += 4 * RL) {
+      const float4 v0 = ld_stream(reinterpret_cast<const float4*>(part + (long long)sp * total + idx));
+      const float4 v1 = ld_stream(reinterpret_cast<const float4*>(part + (long long)(sp + RL) * total + idx));
+      const float4 v2 = ld_stream(reinterpret_cast<const float4*>(part + (long long)(sp + 2 * RL) * total + idx));
+      const float4 v3 = ld_stream(reinterpret_cast<const float4*>(part + (long long)(sp + 3 * RL) * total + idx));
+      s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
+      s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; sp < splits; sp += RL) {
       const float4 v = ld_stream(reinterpret_cast<const float4*>(part + (long long)sp * total + idx));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
@@ -949,8 +959,14 @@ int launch_wgrad_reduce(const float* part, float* dw, int O, int I, int k, int s
   const long long total = (long long)O * I * k * k;
   if ((I & 3) == 0) {
     const long long groups = total / 4;
-    if (splits >= 16) wgrad_reduce_vec_kernel<8><<<(unsigned)ceil_div64(groups * 8, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
-    else wgrad_reduce_vec_kernel<1><<<(unsigned)ceil_div64(groups, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
+    // lanes per output group: enough threads to fill the machine, but at least ~8 splits per lane
+    const long long want_threads = 16LL * 256 * sm_count();
+    if (splits >= 64 || (splits >= 16 && groups * 2 < want_threads / 4))
+      wgrad_reduce_vec_kernel<8><<<(unsigned)ceil_div64(groups * 8, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
+    else if (splits >= 16 && groups < want_threads)
+      wgrad_reduce_vec_kernel<2><<<(unsigned)ceil_div64(groups * 2, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
+    else
+      wgrad_reduce_vec_kernel<1><<<(unsigned)ceil_div64(groups, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
   } else {
     if (splits >= 16) wgrad_reduce_scalar_kernel<32><<<(unsigned)ceil_div64(total * 32, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
     else wgrad_reduce_scalar_kernel<1><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(part, dw, O, I, k, splits);
