@@ -428,6 +428,21 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
     const bool simple_act = p.act == SGK_ACT_NONE || p.act == SGK_ACT_RELU || p.act == SGK_ACT_LRELU;
     const float act_sl = p.act == SGK_ACT_NONE ? 1.f : (p.act == SGK_ACT_RELU ? 0.f : p.slope);
+    if (p.BN == 16) {
+      // thin outputs (Cout <= 16: the generated image, image gradients): one 16-column tile whose first Cout columns are
+      // real; every thread owns one pixel and writes its Cout channels directly (8-64 B per pixel, no transpose)
+      uint32_t v[32];
+      tmem_ld32(lane_addr, v);   // 32 columns are allocated; the upper 16 are never written and never used
+      tmem_ld_wait();
+      const int ry = r_own / p.tw;
+      const int oy = tyv[0] + ry, ox = txv[0] + (r_own - ry * p.tw);
+      if (ry < p.th && oy < P.Hp && ox < P.Wp) {
+        float* dstp = p.out + (((long long)tn[0] * p.Ho + (oy * P.os + P.ooy)) * p.Wo + (ox * P.os + P.oox)) * p.Co;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < p.Co) dstp[c] = act_apply(__uint_as_float(v[c]) + (p.bias != nullptr ? __ldg(p.bias + c) : 0.f), p.act, p.slope);
+      }
+    } else
     for (int qc = 0; qc < nvalid * p.BN; qc += 32) {
       const int q = qc >= p.BN ? 1 : 0;
       const int cc = qc - q * p.BN;
@@ -1023,7 +1038,11 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
                       g.ph[0].iox == 0 && g.Cg == 2 && (g.Co % 32) == 0 && (g.Wi % 2) == 0 && g.ph[0].kstride == 32 &&
                       (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   const bool window_shape = g.transposed_type == 0 && g.nphase == 1 && g.k == 4 && g.ph[0].is == 2 && g.Cg == 2 && (g.Co % 32) == 0;
-  if (!im2col && !window_shape && !tc_thin && ((g.Cg % 32) != 0 || (g.Co % 32) != 0)) return SGK_EUNSUPPORTED;
+  // thin outputs on the TMA tile (opt-in: measured 2x slower than the CUDA-core tile kernel, which reads the gathered tensor
+  // once through shared memory instead of once per tap and phase)
+  static const bool thin_out_tma = getenv("SGK_TC_THIN_TMA") != nullptr && atoi(getenv("SGK_TC_THIN_TMA")) != 0;
+  const bool thin_out = thin_out_tma && (g.Cg % 32) == 0 && g.Co <= 16;   // image-producing / image-gradient layers
+  if (!im2col && !window_shape && !thin_out && !tc_thin && ((g.Cg % 32) != 0 || (g.Co % 32) != 0)) return SGK_EUNSUPPORTED;
   // N tile: a divisor of Cout in {256,128,64,32}, or one 16-wide tile for thin outputs (Cout <= 16: images, logits)
   int BN = pick_bn(g.Co);
   if (BN == 0) {
@@ -1140,7 +1159,8 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
     SGK_LAUNCH_CHECK("conv_window_persist_kernel");
     return SGK_OK;
   }
-  if (im2col || (use_tma && cs == 0 && BN >= 32)) {
+  static const bool thin_tma = getenv("SGK_TC_THIN_TMA") != nullptr && atoi(getenv("SGK_TC_THIN_TMA")) != 0;
+  if (im2col || (use_tma && cs == 0 && (BN >= 32 || (BN == 16 && thin_tma)))) {
     const int is = g.ph[0].is;
     TmaParams q{};
     TmaMaps tm{};
@@ -1178,7 +1198,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
     // (BN = 256 would need all 512 TMEM columns -> one CTA per SM with an exposed epilogue: measured slower)
     static const int mt_minbn = getenv("SGK_TC_MT_MINBN") ? atoi(getenv("SGK_TC_MT_MINBN")) : 32;
     if (!im2col && 2 * BN <= 512 &&
-        (mt_env == 2 || (mt_env == 0 && BN >= mt_minbn && BN <= 128 && all_tiles * (g.Co / BN) >= 2LL * sm_count())))
+        (mt_env == 2 || (mt_env == 0 && BN >= mt_minbn && BN <= 128 && all_tiles * ceil_div(g.Co, BN) >= 2LL * sm_count())))
       q.mt = 2;
     const int tcols = q.mt * BN;
     q.tmem_cols = tcols <= 32 ? 32 : (tcols <= 64 ? 64 : (tcols <= 128 ? 128 : (tcols <= 256 ? 256 : 512)));
@@ -1225,7 +1245,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tma_tc_kernel)");
       tattr = true;
     }
-    dim3 tgrid((unsigned)mt, (unsigned)(g.Co / BN));
+    dim3 tgrid((unsigned)mt, (unsigned)ceil_div(g.Co, BN));
     conv_tma_tc_kernel<<<tgrid, TC_THREADS, tsmem, st>>>(q, tm);
     SGK_LAUNCH_CHECK("conv_tma_tc_kernel");
     return SGK_OK;

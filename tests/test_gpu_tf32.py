@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 def S():
     import os
     os.environ["SGK_TC_THIN"] = "1"   # also exercise the tensor-core tile on thin-channel layers (off by default: slower)
+    os.environ["SGK_TC_THIN_TMA"] = "1"   # ... including the TMA-fed tile with the 16-column thin epilogue
     import supervised_gan_b200 as S
     S.set_precision("tf32")
     yield S
