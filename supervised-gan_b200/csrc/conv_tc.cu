@@ -1606,6 +1606,11 @@ struct WTmaParams {
   int tiles_x, tiles_y;          // per image
   long long T, t_per_split;      // pixel tiles in total / per split
   int TT, Nc, tmem_cols, stages;
+  // patch mode (stride 1): the CTA's TT taps read ONE x patch of (4 + na - 1) x (8 + nb - 1) pixels per 32-channel group
+  // instead of TT shifted 4 x 8 tiles; the tap (ai, bi) operand starts at patch row (kg + ai)*pw + bi (a BASE32B MN-major
+  // descriptor may start at any 128-B pixel row: tools/umma_mn_shift_test.cu)
+  int patch, pw, ph, nb;
+  uint32_t blk_stride;            // bytes between the 32-channel groups of the patch (1024-B multiple)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 3)
@@ -1615,7 +1620,7 @@ conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
   const int ncg = p.Nc >> 5;
-  const uint32_t b_bytes = (uint32_t)p.TT * (uint32_t)ncg * WTC_BLK;
+  const uint32_t b_bytes = p.patch ? (uint32_t)ncg * p.blk_stride : (uint32_t)p.TT * (uint32_t)ncg * WTC_BLK;
   const uint32_t stage_bytes = WTC_A_BYTES + b_bytes;
   const uint32_t bar_base = smem_base + S * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -1694,7 +1699,7 @@ conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constan
     // =============================================================== TMA producer: G tile + TT gathered X tiles per stage
     if (lane == 0) {
       const int per_img = p.tiles_x * p.tiles_y;
-      const uint32_t tx_bytes = WTC_A_BYTES + b_bytes;
+      const uint32_t tx_bytes = WTC_A_BYTES + (p.patch ? (uint32_t)ncg * (uint32_t)(p.pw * p.ph) * 128u : b_bytes);
       for (int st = 0; st < steps; ++st) {
         const int s = st % S;
         mbar_wait(empty_bar(s), (uint32_t)(((st / S) & 1) ^ 1));
@@ -1707,12 +1712,18 @@ conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constan
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) tma_load_4d(abase + g4 * WTC_BLK, &maps.g, mch0 + g4 * 32, tx0, ty0, n, full_bar(s));
         const uint32_t bbase = abase + WTC_A_BYTES;
-        for (int ti = 0; ti < p.TT; ++ti) {
-          const int tap = t0 + ti;
-          const int a = tap / p.k, b = tap - a * p.k;
+        if (p.patch) {
+          const int a0 = t0 / p.k, b0 = (p.TT <= p.k) ? t0 - a0 * p.k : 0;
           for (int cg = 0; cg < ncg; ++cg)
-            tma_load_4d(bbase + (uint32_t)(ti * ncg + cg) * WTC_BLK, &maps.x, c0 + cg * 32, tx0 * p.s + b + p.off,
-                        ty0 * p.s + a + p.off, n, full_bar(s));
+            tma_load_4d(bbase + (uint32_t)cg * p.blk_stride, &maps.x, c0 + cg * 32, tx0 + b0 + p.off, ty0 + a0 + p.off, n, full_bar(s));
+        } else {
+          for (int ti = 0; ti < p.TT; ++ti) {
+            const int tap = t0 + ti;
+            const int a = tap / p.k, b = tap - a * p.k;
+            for (int cg = 0; cg < ncg; ++cg)
+              tma_load_4d(bbase + (uint32_t)(ti * ncg + cg) * WTC_BLK, &maps.x, c0 + cg * 32, tx0 * p.s + b + p.off,
+                          ty0 * p.s + a + p.off, n, full_bar(s));
+          }
         }
       }
     }
@@ -1727,11 +1738,14 @@ conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constan
         const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
         const uint32_t b_addr = a_addr + WTC_A_BYTES;
         for (int ti = 0; ti < p.TT; ++ti) {
+          const int ai = p.patch ? ti / p.nb : 0, bi = p.patch ? ti - ai * p.nb : 0;
 #pragma unroll
-          for (int kg = 0; kg < 4; ++kg)
-            umma_tf32(tmem_acc + (uint32_t)(ti * p.Nc), make_sw128b32_mnmajor_desc(a_addr + kg * 1024, WTC_BLK, 512u),
-                      make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(ti * ncg) * WTC_BLK + kg * 1024, WTC_BLK, 512u), idesc,
+          for (int kg = 0; kg < 4; ++kg) {
+            const uint64_t bdesc = p.patch ? make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(((kg + ai) * p.pw + bi) * 128), p.blk_stride, 512u)
+                                           : make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(ti * ncg) * WTC_BLK + kg * 1024, WTC_BLK, 512u);
+            umma_tf32(tmem_acc + (uint32_t)(ti * p.Nc), make_sw128b32_mnmajor_desc(a_addr + kg * 1024, WTC_BLK, 512u), bdesc, idesc,
                       (uint32_t)((st | kg) != 0));
+          }
         }
         umma_commit(empty_bar(s));
       }
@@ -2049,12 +2063,22 @@ int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* 
                          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     cuuint64_t xd[4] = {(cuuint64_t)e.I, (cuuint64_t)e.Wb, (cuuint64_t)e.Hb, (cuuint64_t)e.N};
     cuuint64_t xs[3] = {(cuuint64_t)e.I * 4, (cuuint64_t)e.Wb * e.I * 4, (cuuint64_t)e.Hb * e.Wb * e.I * 4};
-    cuuint32_t xb[4] = {32u, (cuuint32_t)(WT_W * e.s), (cuuint32_t)(WT_H * e.s), 1u};
+    static const bool patch_on = !(getenv("SGK_WTMA_PATCH") != nullptr && atoi(getenv("SGK_WTMA_PATCH")) == 0);
+    q.patch = 0;
+    if (patch_on && e.s == 1 && w.TT > 1 && ((w.TT <= e.k && e.k % w.TT == 0) || w.TT % e.k == 0)) {
+      const int na = w.TT <= e.k ? 1 : w.TT / e.k;
+      q.nb = w.TT <= e.k ? w.TT : e.k;
+      q.ph = WT_H + na - 1;
+      q.pw = WT_W + q.nb - 1;
+      q.blk_stride = ((uint32_t)(q.pw * q.ph) * 128u + 1023u) & ~1023u;
+      q.patch = 1;
+    }
+    cuuint32_t xb[4] = {32u, (cuuint32_t)(q.patch ? q.pw : WT_W * e.s), (cuuint32_t)(q.patch ? q.ph : WT_H * e.s), 1u};
     cuuint32_t xe[4] = {1u, (cuuint32_t)e.s, (cuuint32_t)e.s, 1u};
     CUresult r2 = encode(&tm.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.x, xd, xs, xb, xe, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(wgrad) failed (%d, %d)", (int)r1, (int)r2); return SGK_ECUDA; }
-    const uint32_t stb = WTC_A_BYTES + (uint32_t)w.TT * (w.Nc / 32) * WTC_BLK;
+    const uint32_t stb = WTC_A_BYTES + (q.patch ? (uint32_t)(w.Nc / 32) * q.blk_stride : (uint32_t)w.TT * (w.Nc / 32) * WTC_BLK);
     while (q.stages > 2 && (size_t)q.stages * stb > 190 * 1024) --q.stages;
     const size_t smem2 = (size_t)q.stages * stb + 8 * (2 * q.stages + 2) + 1024;
     static bool tattr = false;
