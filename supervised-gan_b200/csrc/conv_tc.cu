@@ -1620,7 +1620,10 @@ conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
   const int ncg = p.Nc >> 5;
-  const uint32_t b_bytes = p.patch ? (uint32_t)ncg * p.blk_stride : (uint32_t)p.TT * (uint32_t)ncg * WTC_BLK;
+  // patch == 2 (stride 2, k = 4, TT = 4 or 8): np parity planes (tap-row ai, column parity pb), each 4 x 9 pixels, serve the
+  // two taps b = pb and b = pb + 2 (the second one shifted by one pixel)
+  const int np = p.patch == 2 ? (p.TT / 4) * 2 : 1;
+  const uint32_t b_bytes = p.patch ? (uint32_t)(np * ncg) * p.blk_stride : (uint32_t)p.TT * (uint32_t)ncg * WTC_BLK;
   const uint32_t stage_bytes = WTC_A_BYTES + b_bytes;
   const uint32_t bar_base = smem_base + S * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -1699,7 +1702,7 @@ conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constan
     // =============================================================== TMA producer: G tile + TT gathered X tiles per stage
     if (lane == 0) {
       const int per_img = p.tiles_x * p.tiles_y;
-      const uint32_t tx_bytes = WTC_A_BYTES + (p.patch ? (uint32_t)ncg * (uint32_t)(p.pw * p.ph) * 128u : b_bytes);
+      const uint32_t tx_bytes = WTC_A_BYTES + (p.patch ? (uint32_t)(np * ncg) * (uint32_t)(p.pw * p.ph) * 128u : b_bytes);
       for (int st = 0; st < steps; ++st) {
         const int s = st % S;
         mbar_wait(empty_bar(s), (uint32_t)(((st / S) & 1) ^ 1));
@@ -1712,7 +1715,15 @@ conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constan
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) tma_load_4d(abase + g4 * WTC_BLK, &maps.g, mch0 + g4 * 32, tx0, ty0, n, full_bar(s));
         const uint32_t bbase = abase + WTC_A_BYTES;
-        if (p.patch) {
+        if (p.patch == 2) {
+          const int a0 = t0 / 4;
+          for (int pl = 0; pl < np; ++pl) {
+            const int ai = pl >> 1, pb = pl & 1;
+            for (int cg = 0; cg < ncg; ++cg)
+              tma_load_4d(bbase + (uint32_t)(pl * ncg + cg) * p.blk_stride, &maps.x, c0 + cg * 32, tx0 * 2 + pb + p.off,
+                          ty0 * 2 + a0 + ai + p.off, n, full_bar(s));
+          }
+        } else if (p.patch) {
           const int a0 = t0 / p.k, b0 = (p.TT <= p.k) ? t0 - a0 * p.k : 0;
           for (int cg = 0; cg < ncg; ++cg)
             tma_load_4d(bbase + (uint32_t)cg * p.blk_stride, &maps.x, c0 + cg * 32, tx0 + b0 + p.off, ty0 + a0 + p.off, n, full_bar(s));
@@ -1741,8 +1752,13 @@ conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constan
           const int ai = p.patch ? ti / p.nb : 0, bi = p.patch ? ti - ai * p.nb : 0;
 #pragma unroll
           for (int kg = 0; kg < 4; ++kg) {
-            const uint64_t bdesc = p.patch ? make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(((kg + ai) * p.pw + bi) * 128), p.blk_stride, 512u)
-                                           : make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(ti * ncg) * WTC_BLK + kg * 1024, WTC_BLK, 512u);
+            uint64_t bdesc;
+            if (p.patch == 2)   // plane (ai, bi & 1), shifted by bi >> 1 pixels; k-group kg = plane row kg
+              bdesc = make_sw128b32_mnmajor_desc(b_addr + (uint32_t)((ai * 2 + (bi & 1)) * ncg) * p.blk_stride +
+                                                     (uint32_t)((kg * p.pw + (bi >> 1)) * 128), p.blk_stride, 512u);
+            else
+              bdesc = p.patch ? make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(((kg + ai) * p.pw + bi) * 128), p.blk_stride, 512u)
+                              : make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(ti * ncg) * WTC_BLK + kg * 1024, WTC_BLK, 512u);
             umma_tf32(tmem_acc + (uint32_t)(ti * p.Nc), make_sw128b32_mnmajor_desc(a_addr + kg * 1024, WTC_BLK, 512u), bdesc, idesc,
                       (uint32_t)((st | kg) != 0));
           }
@@ -2073,12 +2089,20 @@ int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* 
       q.blk_stride = ((uint32_t)(q.pw * q.ph) * 128u + 1023u) & ~1023u;
       q.patch = 1;
     }
-    cuuint32_t xb[4] = {32u, (cuuint32_t)(q.patch ? q.pw : WT_W * e.s), (cuuint32_t)(q.patch ? q.ph : WT_H * e.s), 1u};
+    static const bool patch2_on = getenv("SGK_WTMA_PATCH2") != nullptr && atoi(getenv("SGK_WTMA_PATCH2")) != 0;
+    if (patch2_on && e.s == 2 && e.k == 4 && (w.TT == 4 || w.TT == 8)) {
+      // stride 2: parity planes of 4 x 9 pixels (traversal stride 2), two taps per plane
+      q.nb = 4; q.ph = WT_H; q.pw = WT_W + 1;
+      q.blk_stride = ((uint32_t)(q.pw * q.ph) * 128u + 1023u) & ~1023u;
+      q.patch = 2;
+    }
+    cuuint32_t xb[4] = {32u, (cuuint32_t)(q.patch ? q.pw * e.s : WT_W * e.s), (cuuint32_t)(q.patch ? q.ph * e.s : WT_H * e.s), 1u};
     cuuint32_t xe[4] = {1u, (cuuint32_t)e.s, (cuuint32_t)e.s, 1u};
     CUresult r2 = encode(&tm.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.x, xd, xs, xb, xe, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(wgrad) failed (%d, %d)", (int)r1, (int)r2); return SGK_ECUDA; }
-    const uint32_t stb = WTC_A_BYTES + (q.patch ? (uint32_t)(w.Nc / 32) * q.blk_stride : (uint32_t)w.TT * (w.Nc / 32) * WTC_BLK);
+    const uint32_t nplanes = q.patch == 2 ? (uint32_t)(w.TT / 4) * 2u : 1u;
+    const uint32_t stb = WTC_A_BYTES + (q.patch ? nplanes * (uint32_t)(w.Nc / 32) * q.blk_stride : (uint32_t)w.TT * (w.Nc / 32) * WTC_BLK);
     while (q.stages > 2 && (size_t)q.stages * stb > 190 * 1024) --q.stages;
     const size_t smem2 = (size_t)q.stages * stb + 8 * (2 * q.stages + 2) + 1024;
     static bool tattr = false;
