@@ -160,7 +160,7 @@ def run_ours(args):
                                    [p for d in m.netD for p in d.parameters()])
         if os.environ.get("SGK_OVERLAP_COMM", "1") != "0":
             # one bucket per discriminator scale (their backward passes run one after the other), two for the generator
-            m.grad_sync = sdist.OverlappedGradSync(world, {"D": [list(d.parameters()) for d in m.netD],
+            m.grad_sync = sdist.OverlappedGradSync(world, {"D": [list(d.model.parameters()) for d in m.netD],
                                                            "G": sdist.size_split(list(m.netG.parameters()))})
         else:
             m.grad_sync = sdist.GradSync(world)

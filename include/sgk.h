@@ -207,6 +207,18 @@ int sgk_l1_loss(const float* x, const float* y, const float* w, size_t n, float*
 int sgk_bce_pair_loss(const float* x, const float* t, size_t n, float* loss_out, float* grad,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- image history buffer
+ * ImagePool.query (util/image_pool.py:13-33; fcgan_model.py:147, cgan_model.py:162, twostage_cycle_model.py:214,228,234):
+ * for b = 0..B-1 IN ORDER, with code = plan_dev[b] (device int32, written by the host from the reference's own
+ * `random.uniform` / `random.randint` draws):
+ *   code < 0          out[b] = images[b]                                  (rejected, or pool_size == 0)
+ *   code = 2*slot     pool[slot] = images[b]; out[b] = images[b]          (pool still filling)
+ *   code = 2*slot+1   out[b] = pool[slot];   pool[slot] = images[b]       (swap)
+ * images / out: [B][per_image] floats, pool: [pool_size][per_image] floats, all device memory.  Sequential semantics
+ * within the batch are preserved when several images hit the same slot. */
+int sgk_image_pool_query(const float* images, float* pool, const int32_t* plan_dev, float* out, int B,
+                         long long per_image, int pool_size, void* stream);
+
 /* ---------------------------------------------------------------- optimiser
  * torch.optim.Adam (fcgan_model.py:98-109; cgan_model.py:95-108; twostage_cycle_model.py:149-166):
  * multi-tensor launches (metadata passed by value as kernel parameters, so a captured CUDA graph carries it).

@@ -7,6 +7,26 @@ import torch
 from . import networks, ops
 
 
+def save_optimizer(optimizer, save_dir, label, epoch_label):
+    """'<epoch>_optim_<label>.pth' next to the reference's '<epoch>_net_<label>.pth' files (base_model.py:44-52 saves the
+    networks only, so a resumed reference run restarts Adam cold): exp_avg / exp_avg_sq / step per parameter and the
+    param_groups, as CPU tensors."""
+    os.makedirs(save_dir, exist_ok=True)
+    sd = optimizer.state_dict()
+    state = {k: {n: (v.detach().cpu() if torch.is_tensor(v) else v) for n, v in st.items()} for k, st in sd['state'].items()}
+    torch.save({'state': state, 'param_groups': sd['param_groups']}, os.path.join(save_dir, '%s_optim_%s.pth' % (epoch_label, label)))
+
+
+def load_optimizer(optimizer, save_dir, label, epoch_label, device, required=False):
+    path = os.path.join(save_dir, '%s_optim_%s.pth' % (epoch_label, label))
+    if not os.path.exists(path):
+        if required:
+            raise FileNotFoundError(path)
+        return False
+    optimizer.load_state_dict(torch.load(path, map_location=device))
+    return True
+
+
 class BaseModel(object):
     def name(self):
         return 'BaseModel'
@@ -83,6 +103,16 @@ class BaseModel(object):
         save_path = os.path.join(model_dir or self.save_dir, save_filename)
         network.load_state_dict(torch.load(save_path, map_location=self.device))
         ops.bump_weights_epoch()
+
+    def save_optimizers(self, label):
+        for name, o in self._optimizers().items():
+            save_optimizer(o, self.save_dir, name, label)
+
+    def load_optimizers(self, label, required=False):
+        return all([load_optimizer(o, self.save_dir, name, label, self.device, required) for name, o in self._optimizers().items()])
+
+    def _optimizers(self):
+        return {k[len('optimizer_'):]: v for k, v in vars(self).items() if k.startswith('optimizer_')}
 
     def _decay(self, optimizers, old, base):
         lr = old - base / self.opt.niter_decay

@@ -158,6 +158,8 @@ class CGANModel(BaseModel):
         self.save_network(self.netG, 'G', label, gpu_ids=self.gpu_ids)
         for n, netD in enumerate(self.netD):
             self.save_network(netD, 'D_%d' % n, label, gpu_ids=self.gpu_ids)
+        if getattr(self.opt, "save_optimizer_state", True):
+            self.save_optimizers(label)
 
     def update_learning_rate(self):
         self.old_lr = self._decay([self.optimizer_D, self.optimizer_G], self.old_lr, self.opt.lr)

@@ -17,12 +17,15 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
+from . import ops
 
 
 def broadcast_parameters(tensors, src=0):
-    """Initial weight synchronisation (the reference re-broadcasts the replica on every forward)."""
+    """Weight synchronisation (the reference re-broadcasts the replica on every forward).  The broadcast writes parameter
+    memory behind autograd's back (no Tensor._version bump), so every packed-weight / tap cache is invalidated."""
     for t in tensors:
         dist.broadcast(t.data if isinstance(t, torch.nn.Parameter) else t, src)
+    ops.bump_weights_epoch()
 
 
 def cuda_packer(grads, flat):
@@ -87,6 +90,7 @@ class OverlappedGradSync(GradSync):
         self._owner = {}
         self._active = None
         self._count, self._launched, self._inflight = [], [], []
+        self._dirty = []
         self._handles = []
         for tag, bl in self.buckets.items():
             for bi, plist in enumerate(bl):
@@ -101,13 +105,19 @@ class OverlappedGradSync(GradSync):
         self._active = tag
         self._count = [len(plist) for plist in self.buckets[tag]]
         self._launched = [False] * len(self._count)
+        self._dirty = [False] * len(self._count)
         self._inflight = []
 
     def _hook(self, p):
         if self._active is None:
             return
         tag, bi = self._owner.get(id(p), (None, None))
-        if tag != self._active or self._launched[bi]:
+        if tag != self._active:
+            return
+        if self._launched[bi]:
+            # a second backward() of the same phase added to a gradient that was already packed and reduced: the
+            # bucket is re-packed and re-reduced in __call__ (the early result is discarded, never silently kept)
+            self._dirty[bi] = True
             return
         self._count[bi] -= 1
         if self._count[bi] == 0:
@@ -128,16 +138,26 @@ class OverlappedGradSync(GradSync):
         grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in params if p.grad is not None]
         self.packer(grads, flat)
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._inflight.append((work, params, layout, flat))
+        self._inflight.append((work, params, layout, flat, bi))
 
     def __call__(self, params, tag):
         if self._active != tag:
             return super().__call__(params, tag)       # not armed for this phase: one bucket, synchronous
+        if any(self._dirty):
+            keep = []
+            for ent in self._inflight:
+                ent[0].wait()
+                if not self._dirty[ent[4]]:
+                    keep.append(ent)
+            self._inflight = keep
+            for bi, d in enumerate(self._dirty):
+                if d:
+                    self._launched[bi] = False      # relaunched below from the final gradients
         for bi, done in enumerate(self._launched):
             if not done:
                 self._launch(tag, bi)
         covered = set()
-        for work, plist, layout, flat in self._inflight:
+        for work, plist, layout, flat, _ in self._inflight:
             work.wait()
             for p, lay in zip(plist, layout):
                 covered.add(id(p))

@@ -17,6 +17,7 @@ from collections import OrderedDict
 import torch
 
 from . import networks, ops
+from .base_model import load_optimizer, save_optimizer
 from .image_pool import ImagePool
 from .optim import FusedAdam
 
@@ -47,7 +48,10 @@ class FCGANModel(object):
         opt.input_nc = len(self.chnl_idx_input)
 
         dev = self.device
-        self.input = torch.empty(opt.batchSize, opt.input_nc, opt.fineSize, opt.fineSize, device=dev)
+        # D(fake.detach()) and D(real) run as one 2B batch: the real half of that batch IS the input buffer (set_input
+        # copies straight into it) and the image pool writes the fake half, so no torch.cat is needed
+        self._both = torch.empty(2 * opt.batchSize, opt.input_nc, opt.fineSize, opt.fineSize, device=dev)
+        self.input = self._both[opt.batchSize:]
         self.noise = None
         self.noise_ = torch.empty(opt.batchSize, opt.noise_nc, opt.noiseSize, opt.noiseSize, device=dev)
         self.fixed_noiseA = torch.empty_like(self.noise_).normal_(0, 1)
@@ -86,13 +90,18 @@ class FCGANModel(object):
             self.optimizer_D = FusedAdam(params, lr=opt.lr, betas=(opt.beta1, 0.999), grad_scale=grad_scale)
             self.params_D = [p for netD in self.netD for p in netD.model.parameters()]
             self.params_G = list(self.netG.parameters())
+            if opt.continue_train:
+                # optimiser moments and step counts, when a previous run of THIS framework saved them (see save())
+                load_optimizer(self.optimizer_G, self.save_dir, 'G', opt.which_epoch, self.device)
+                load_optimizer(self.optimizer_D, self.save_dir, 'D', opt.which_epoch, self.device)
         self.batch_D_passes = getattr(opt, "batch_D_passes", True) and opt.norm == 'instance'
         self.skip_unused_grads = getattr(opt, "skip_unused_grads", True)
         self.grad_sync = None  # data-parallel hook: callable(list_of_params, tag) run between backward and step
         # opt.cuda_graph: after `graph_warmup` eager steps the whole step (G fwd, D phase, Adam, G phase, Adam -- and the
         # NCCL all-reduces under data parallelism) is captured once and replayed; nothing in the step touches the host.
-        # Requires pool_size == 0 (the image pool draws from Python's `random`) and a fixed batch shape.
-        self.use_graph = bool(getattr(opt, "cuda_graph", False)) and self.isTrain and opt.pool_size == 0
+        # Requires a fixed batch shape.  The image pool's decisions are drawn on the host before every replay and read by
+        # the captured pool kernel from device memory (image_pool.py), so pool_size > 0 is captured as well.
+        self.use_graph = bool(getattr(opt, "cuda_graph", False)) and self.isTrain
         self._graph = None
         self._side = None
         self._stage = None
@@ -114,7 +123,7 @@ class FCGANModel(object):
                 if self._graph is not None:
                     raise RuntimeError("cuda_graph: the batch shape is frozen after capture (got %s, captured %s)"
                                        % (shape, tuple(self.input.shape)))
-                self.input = torch.empty(shape, device=self.device)
+                self._new_input(shape)
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream()
             cs = self._copy_stream
@@ -141,9 +150,22 @@ class FCGANModel(object):
             if self._graph is not None:
                 raise RuntimeError("cuda_graph: the batch shape is frozen after capture (got %s, captured %s)"
                                    % (tuple(data.shape), tuple(self.input.shape)))
-            self.input = torch.empty(data.shape, device=self.device)
+            self._new_input(data.shape)
         self.input.copy_(data, non_blocking=True)
         self.image_paths = input['A_paths' if AorB else 'B_paths']
+
+    def _new_input(self, shape):
+        self._both = torch.empty((2 * shape[0],) + tuple(shape[1:]), device=self.device)
+        self.input = self._both[shape[0]:]
+
+    def _both_batch(self, real):
+        """The 2B buffer whose second half holds `real` (no copy when `real` is the input buffer itself)."""
+        B = real.shape[0]
+        if self._both is None or self._both.shape[0] != 2 * B or self._both.shape[1:] != real.shape[1:]:
+            self._both = torch.empty((2 * B,) + tuple(real.shape[1:]), device=self.device)
+        if real.data_ptr() != self._both[B:].data_ptr():
+            self._both[B:].copy_(real)          # a caller replaced self.input: one device-to-device copy
+        return self._both
 
     def _draw_noise(self):
         o = self.opt
@@ -170,18 +192,19 @@ class FCGANModel(object):
 
     # ------------------------------------------------------------------ the two phases (fcgan_model.py:146-176)
     def backward_D(self):
-        fake = self.fake_pool.query(self.fake)
         real = self.real
         self.loss_D_fake = 0
         self.loss_D_real = 0
-        if self.batch_D_passes and fake.shape == real.shape:
-            both = torch.cat([fake.detach(), real], 0)
-            B = fake.shape[0]
+        if self.batch_D_passes and self.fake.shape == real.shape:
+            B = real.shape[0]
+            both = self._both_batch(real)
+            self.fake_pool.query(self.fake, out=both[:B])     # the pool kernel writes the fake half in place
             for netD in self.netD:
                 pred = netD.forward(both)
                 self.loss_D_fake = self.loss_D_fake + self.criterionGAN(pred[:B], False)
                 self.loss_D_real = self.loss_D_real + self.criterionGAN(pred[B:], True)
         else:
+            fake = self.fake_pool.query(self.fake)
             for netD in self.netD:
                 self.loss_D_fake = self.loss_D_fake + self.criterionGAN(netD.forward(fake.detach()), False)
             for netD in self.netD:
@@ -218,6 +241,11 @@ class FCGANModel(object):
         # two graphs: the generator forward does not read the real batch, so the H2D copy of set_input (on its own stream)
         # overlaps it; the update phases are ordered after the copy
         g_fwd, g_upd = self._graph
+        # the captured Adam kernels read lr / betas / grad_scale from device memory: push host-side changes
+        # (update_learning_rate) before replaying -- a tuple compare, and one small H2D copy only when something changed
+        self.optimizer_D.sync_hyper()
+        self.optimizer_G.sync_hyper()
+        self.fake_pool.prepare_replay()          # this step's pool decisions (Python `random`, the reference's order)
         g_fwd.replay()
         self._wait_input()
         g_upd.replay()
@@ -308,6 +336,9 @@ class FCGANModel(object):
         self.save_network(self.netG, 'G', label, gpu_ids=self.gpu_ids)
         for netD, n in zip(self.netD, range(self.n_netD)):
             self.save_network(netD, 'D_%d' % n, label, self.gpu_ids)
+        if getattr(self.opt, "save_optimizer_state", True):
+            save_optimizer(self.optimizer_G, self.save_dir, 'G', label)
+            save_optimizer(self.optimizer_D, self.save_dir, 'D', label)
 
     def update_learning_rate(self):
         lrd = self.opt.lr / self.opt.niter_decay

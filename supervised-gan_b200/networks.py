@@ -458,7 +458,7 @@ class NLayerDiscriminator(nn.Module):
         """Diagonal of gauss_filter.0.weight as [C, k, k]; the fused blur+decimate kernel is channel-diagonal.
         A filter with non-zero off-diagonal blocks (never produced by define_D) is rejected loudly."""
         w = self.gauss_filter[0].weight
-        tag = (w._version, w.data_ptr())
+        tag = (w._version, w.data_ptr(), ops.weights_epoch())   # epoch: out-of-band writes (broadcast, load_state_dict)
         if self._taps is None or self._taps[0] != tag:
             wd = w.detach()
             C = wd.shape[0]

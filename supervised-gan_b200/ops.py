@@ -33,6 +33,10 @@ _param_epoch = {}     # data_ptr -> epoch of the last out-of-band update of that
 _epoch_counter = 0
 
 
+def weights_epoch():
+    return _weights_epoch
+
+
 def bump_weights_epoch(params=None):
     """Invalidate packed-weight caches after parameter memory changed behind autograd's back (fused optimiser,
     load_state_dict, weights_init, graph replays).  With `params` only those tensors' caches are invalidated -- Adam(D) must
@@ -308,6 +312,10 @@ class _ConvFn(torch.autograd.Function):
         # a conv bias that feeds an Instance/BatchNorm has an exactly-zero gradient (the norm removes the mean);
         # we emit exact zeros instead of the reference's ~1e-9 rounding noise (DESIGN.md "deviations")
         ctx.act, ctx.slope, ctx.bias_grad_zero = act, slope, bias_grad_zero
+        # The weight is referenced, not saved through save_for_backward: the backward kernels consume the PACKED copy, which
+        # is refreshed by the fused optimiser (an in-place update autograd's version counter would reject although every
+        # step driver of the reference only steps after backward).  Consequence, by design: dgrad uses the weights as of
+        # backward time; do not step an optimiser between a forward and its backward.
         ctx.weight_ref = weight
         ctx.save_for_backward(x, y if act != L.ACT_NONE else None)
         return y
@@ -703,8 +711,15 @@ class _LossFn(torch.autograd.Function):
             L.check(lib.sgk_gan_loss(_p(x), n, mode, target, _p(out), _p(grad), _p(ws), ws.numel(), st), "gan_loss")
         elif kind == "l1":
             y = _chk(y.detach(), "l1 target")
+            if w is not None and w.shape != x.shape:
+                # the reference's torch.mul(|x - y|, w) broadcasts an (N,1,H,W) weight map over the channels
+                # (networks.py:205-214 with cgan_model.py:197-206 and output_nc > 1)
+                try:
+                    w = w.detach().expand_as(x)
+                except RuntimeError:
+                    raise RuntimeError("l1 loss: weight of shape %s does not broadcast to %s" % (tuple(w.shape), tuple(x.shape)))
             w = _chk(w.detach(), "l1 weight") if w is not None else None
-            if y.shape != x.shape or (w is not None and w.shape != x.shape):
+            if y.shape != x.shape:
                 raise RuntimeError("l1 loss: shapes differ")
             L.check(lib.sgk_l1_loss(_p(x), _p(y), _p(w), n, _p(out), _p(grad), _p(ws), ws.numel(), st), "l1_loss")
         else:

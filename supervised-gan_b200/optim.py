@@ -3,7 +3,8 @@
 Replaces `torch.optim.Adam(params, lr, betas=(beta1, 0.999))` as the reference's step drivers build it
 (fcgan_model.py:98-109; cgan_model.py:95-108; twostage_cycle_model.py:149-166): same update rule
 (eps 1e-8, no weight decay, no amsgrad), same `param_groups[i]['lr']` protocol for
-`update_learning_rate`, `state_dict()` with `exp_avg` / `exp_avg_sq` / `step` per parameter.
+`update_learning_rate`, `state_dict()` with `exp_avg` / `exp_avg_sq` / `step` per parameter (`step` is a view
+of the group's device-side counter, so a resumed optimiser continues its bias correction where it stopped).
 One kernel launch per ~36 tensors; the step counter and hyper-parameters live on the device so the
 whole training step can be captured in a CUDA graph.  `grad_scale` (1/world under data parallelism)
 is folded into the same kernel.
@@ -62,7 +63,14 @@ class FusedAdam(torch.optim.Optimizer):
                 if "exp_avg" not in s:
                     s["exp_avg"] = torch.zeros_like(p)
                     s["exp_avg_sq"] = torch.zeros_like(p)
-                s["_g"] = g  # keep alive until the launch is ordered on the stream
+                if s.get("step") is not st["step"]:
+                    # torch.optim.Adam's per-parameter `step` entry: every parameter of the group shares the group's
+                    # device counter (saved by state_dict(), adopted again by load_state_dict())
+                    if "step" in s and int(s["step"]) != int(st["step"]) and not torch.cuda.is_current_stream_capturing():
+                        st["step"].fill_(int(s["step"]))       # resumed from a checkpoint
+                    s["step"] = st["step"]
+                # the launch below is stream-ordered and the caching allocator is stream-safe: the gradient needs no
+                # extra reference (one kept in `state` would be serialised by state_dict() and double gradient memory)
                 entries.append((p.data_ptr(), g.data_ptr(), s["exp_avg"].data_ptr(), s["exp_avg_sq"].data_ptr(), p.numel()))
             if not entries:
                 continue

@@ -259,6 +259,8 @@ class TwoStageCycleModel(BaseModel):
         for lab, lst in (('D1', self.netD1), ('D2', self.netD2)):
             for n, netD in enumerate(lst):
                 self.save_network(netD, '%s_%d' % (lab, n), label, gpu_ids=self.gpu_ids)
+        if getattr(self.opt, "save_optimizer_state", True):
+            self.save_optimizers(label)
 
     def update_learning_rate(self):
         # twostage_cycle_model.py:480-503: per-group linear decay
