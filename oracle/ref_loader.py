@@ -17,7 +17,10 @@ import sys
 import types
 import argparse
 
-REF_ROOT = os.environ.get("SGK_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+# /root/reference in the build container; on the GPU box the byte-for-byte copy made by oracle/vendor_ref.py
+REF_ROOT = os.environ.get("SGK_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/models/networks.py") else _VENDORED)
 
 
 def available():

@@ -42,6 +42,14 @@ class BaseModel(object):
         self.model_dir = getattr(opt, "pretrained_model_dir", "")
         self.grad_sync = None  # data-parallel hook: callable(list_of_params, tag) between backward and step
         self.skip_unused_grads = getattr(opt, "skip_unused_grads", True)
+        # opt.cuda_graph: after `graph_warmup` eager steps (on a side stream) the whole step -- every network pass, loss,
+        # optimiser and, under data parallelism, the NCCL all-reduces -- is captured once and replayed; nothing in a step
+        # touches the host.  Requires fixed batch shapes (set_input copies into the captured input buffers).
+        self.use_graph = bool(getattr(opt, "cuda_graph", False)) and self.isTrain
+        self._graph = None
+        self._side = None
+        self._eager_steps = 0
+        self._graph_warmup = int(getattr(opt, "graph_warmup", 3))
 
     @staticmethod
     def parse_channels(which_channel):
@@ -85,6 +93,45 @@ class BaseModel(object):
             if self.enabled:
                 for p in self.params:
                     p.requires_grad_(True)
+
+    # ------------------------------------------------------------------ step execution (eager / CUDA graph)
+    def optimize_parameters(self):
+        """The reference's optimize_parameters (cgan_model.py:210-225, twostage_cycle_model.py:412-438) is the subclass's
+        `_optimize_parameters_eager`; this wrapper adds the capture / replay protocol of opt.cuda_graph."""
+        if self._graph is not None:
+            self._replay()
+            return
+        if self.use_graph and self._eager_steps >= self._graph_warmup:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._optimize_parameters_eager()
+            self._graph = g
+            self._replay()          # capture does not execute: run the step this call stands for
+            return
+        self._eager_steps += 1
+        if self.use_graph:
+            # warm-up steps of graph mode run on a side stream: autograd's AccumulateGrad nodes remember the stream they
+            # were created on, and the legacy default stream cannot be joined from a capturing stream
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._optimize_parameters_eager()
+            cur.wait_stream(self._side)
+            return
+        self._optimize_parameters_eager()
+
+    def _replay(self):
+        # captured Adam kernels read lr / betas / grad_scale from device memory, captured pool kernels read their plans
+        for o in self._optimizers().values():
+            o.sync_hyper()
+        for k, v in vars(self).items():
+            if k.startswith('fake_pool'):
+                v.prepare_replay()
+        self._graph.replay()
+        ops.bump_weights_epoch()
 
     def _step(self, optimizer, params, tag):
         if self.grad_sync is not None:

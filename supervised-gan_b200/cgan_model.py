@@ -129,7 +129,7 @@ class CGANModel(BaseModel):
             self.loss_G = self.loss_G + self.loss_G_L1
             self.loss_G.backward()
 
-    def optimize_parameters(self):
+    def _optimize_parameters_eager(self):
         self.forward()
         for _ in range(self.opt.n_update_D):
             self.optimizer_D.zero_grad(set_to_none=True)

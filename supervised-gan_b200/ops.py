@@ -107,40 +107,76 @@ def _stream():
 
 
 class KernelTimer:
-    """Optional per-launch CUDA-event timing of the conv kernels (bench.py's roofline leg).  Events are recorded on
-    the stream the kernel is launched on; nothing is synchronised until `summary()`."""
+    """Per-kernel timing for bench.py's roofline leg, free of host gaps.
+
+    While installed (`set_kernel_timer`), every instrumented C-ABI call of a step is RECORDED as a replayable closure
+    (its tensors stay alive with it) together with its algorithmic work (FLOPs, bytes) and the names of the kernels it
+    launched.  `measure()` then replays one representative call per distinct tag `reps` times back to back from a CUDA
+    graph -- no Python, no launch gaps -- bracketed by CUDA events on the launching stream.  Two numbers per call:
+    `warm_us` (inputs hot in L2 from the previous replay) and `cold_us` (a > L2-sized buffer is rewritten before every
+    replay; the rewrite-only graph is timed separately and subtracted)."""
+
+    FLUSH_BYTES = 256 << 20
 
     def __init__(self):
-        self.records = []
+        self.records = []      # (tag, flops, bytes, fn(stream), kernels)
 
-    def time(self, tag, flops, fn):
+    def call(self, tag, flops, nbytes, fn):
         lib = L.load()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         lib.sgk_trace_kernels(1)          # per-thread: backward calls arrive on the autograd engine's thread
-        a.record()
-        rc = fn()
-        b.record()
+        rc = fn(_stream())
         kern = (lib.sgk_traced_kernels() or b"").decode()
         lib.sgk_trace_kernels(0)
-        self.records.append((tag, flops, a, b, kern))
+        self.records.append((tag, float(flops), float(nbytes), fn, kern))
         return rc
 
-    def summary(self, by="tag"):
-        """by='tag': per layer and pass; by='kernel': per main kernel (first kernel each call launched)."""
+    @staticmethod
+    def _time_graph(body, reps, iters=3):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                body(torch.cuda.current_stream().cuda_stream)
+        best = None
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g.replay()
+            b.record()
+            b.synchronize()
+            t = a.elapsed_time(b) * 1e3 / reps
+            best = t if best is None else min(best, t)
+        del g
+        return best
+
+    def measure(self, reps=10, cold=True):
+        """{tag: {calls, flops, bytes, kernels, warm_us, cold_us}} -- times are per call."""
         torch.cuda.synchronize()
         out = {}
-        for tag, flops, a, b, kern in self.records:
-            if by == "tag":
-                key = tag
+        for tag, flops, nbytes, fn, kern in self.records:
+            e = out.get(tag)
+            if e is None:
+                out[tag] = {"calls": 1, "flops": flops, "bytes": nbytes, "kernels": kern, "_fn": fn}
             else:
-                names = [k for k in kern.split("+") if k]
-                main = [k for k in names if k.startswith(("conv_", "gather_", "edge_", "pixel_reduce"))]
-                key = (main or names or ["?"])[0]
-            e = out.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0})
-            e["launches"] += 1
-            e["ms"] += a.elapsed_time(b)
-            e["flops"] += flops
+                e["calls"] += 1
+        flush = torch.empty(self.FLUSH_BYTES // 4, dtype=torch.float32, device="cuda") if cold else None
+        flush_us = self._time_graph(lambda st: flush.zero_(), reps) if cold else 0.0
+        for tag, e in out.items():
+            fn = e.pop("_fn")
+            e["warm_us"] = self._time_graph(fn, reps)
+            if cold:
+                def body(st, fn=fn):
+                    flush.zero_()
+                    fn(st)
+                e["cold_us"] = max(self._time_graph(body, reps) - flush_us, 0.0)
+            else:
+                e["cold_us"] = None
         return out
+
+    @staticmethod
+    def main_kernel(kern):
+        names = [k for k in kern.split("+") if k]
+        main = [k for k in names if k.startswith(("conv_", "gather_", "edge_", "pixel_reduce"))]
+        return (main or names or ["?"])[0]
 
 
 _timer = None
@@ -151,8 +187,9 @@ def set_kernel_timer(t):
     _timer = t
 
 
-def _timed(tag, flops, fn):
-    return fn() if _timer is None else _timer.time(tag, flops, fn)
+def _timed(tag, flops, nbytes, fn):
+    """fn(stream) -> rc.  Instrumentation point of the roofline leg (see KernelTimer); a plain call otherwise."""
+    return fn(_stream()) if _timer is None else _timer.call(tag, flops, nbytes, fn)
 
 
 def _conv_tag(op, d):
@@ -164,6 +201,11 @@ def _conv_flops(d):
     if d.transposed:
         return 2.0 * d.N * d.Hin * d.Win * d.Cin * d.Cout * d.k * d.k
     return 2.0 * d.N * d.Hout * d.Wout * d.Cin * d.Cout * d.k * d.k
+
+
+def _conv_bytes(d):
+    """Algorithmic HBM bytes of one conv pass: both activation tensors once + the weights once (fp32)."""
+    return 4.0 * (d.N * d.Hin * d.Win * d.Cin + d.N * d.Hout * d.Wout * d.Cout + d.Cin * d.Cout * d.k * d.k)
 
 
 def _chk(t, name="tensor"):
@@ -282,7 +324,7 @@ class _ConvFn(torch.autograd.Function):
             st = _stream()
             desc1, _, wp1, _ = cfg.tap_weights(w, x.shape)
             t = torch.empty((desc.N, desc.Hin, desc.Win, 32), dtype=torch.float32, device=x.device)
-            L.check(_timed(_conv_tag("fwd", desc1), _conv_flops(desc1), lambda: lib.sgk_conv_fwd(
+            L.check(_timed(_conv_tag("fwd", desc1), _conv_flops(desc1), _conv_bytes(desc1), lambda st: lib.sgk_conv_fwd(
                 ctypes.byref(desc1), _p(x), _p(wp1), None, _p(t), L.ACT_NONE, 0.0, st)), "conv_fwd(tap 1x1)")
             L.check(lib.sgk_tap_fold_fwd(_p(t), _p(b), _p(y), desc.N, desc.Hin, desc.Win, desc.Cout, desc.k, desc.pad, act,
                                          slope, st), "tap_fold_fwd")
@@ -299,14 +341,14 @@ class _ConvFn(torch.autograd.Function):
                 descp = L.SgkConvDesc(desc.N, desc.Cin, desc.Hin + 2 * pd, desc.Win + 2 * pd, desc.Cout, desc.Hout, desc.Wout,
                                       desc.k, desc.stride, 0, 0, desc.precision)
             wp = cfg.packed(weight, desc, L.OP_FWD)      # the packed layout does not depend on the padding
-            L.check(_timed(_conv_tag("fwd", descp), _conv_flops(descp), lambda: lib.sgk_conv_fwd(
+            L.check(_timed(_conv_tag("fwd", descp), _conv_flops(descp), _conv_bytes(descp), lambda st: lib.sgk_conv_fwd(
                 ctypes.byref(descp), _p(xp), _p(wp), _p(b), _p(y), act, slope, st)), "conv_fwd(padded)")
             ctx.descp = descp
             x = xp                                        # the weight gradient is taken from the padded copy as well
         else:
             wp = cfg.packed(weight, desc, L.OP_FWD)
-            L.check(_timed(_conv_tag("fwd", desc), _conv_flops(desc), lambda: lib.sgk_conv_fwd(
-                ctypes.byref(desc), _p(x), _p(wp), _p(b), _p(y), act, slope, _stream())), "conv_fwd")
+            L.check(_timed(_conv_tag("fwd", desc), _conv_flops(desc), _conv_bytes(desc), lambda st: lib.sgk_conv_fwd(
+                ctypes.byref(desc), _p(x), _p(wp), _p(b), _p(y), act, slope, st)), "conv_fwd")
         ctx.x_shape = (desc.N, desc.Hin, desc.Win, desc.Cin)
         ctx.cfg, ctx.desc, ctx.has_bias = cfg, desc, bias is not None
         # a conv bias that feeds an Instance/BatchNorm has an exactly-zero gradient (the norm removes the mean);
@@ -338,7 +380,7 @@ class _ConvFn(torch.autograd.Function):
             gw = torch.empty_like(weight)
             gbf = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device) if want_b else None
             ws = _ws(lib.sgk_conv_wgrad_workspace_bytes(ctypes.byref(wdesc)), dy.device)
-            rc = _timed(_conv_tag("wgrad", wdesc), _conv_flops(wdesc), lambda: lib.sgk_conv_wgrad_act(
+            rc = _timed(_conv_tag("wgrad", wdesc), _conv_flops(wdesc), _conv_bytes(wdesc) + 4.0 * y.numel(), lambda st: lib.sgk_conv_wgrad_act(
                 ctypes.byref(wdesc), _p(x), _p(dy), _p(y), ctx.act, ctx.slope, _p(gw), _p(gbf), _p(ws), ws.numel(), st))
             if rc == 0:
                 if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -357,13 +399,13 @@ class _ConvFn(torch.autograd.Function):
             L.check(lib.sgk_tap_unfold(_p(dy), _p(g32), desc.N, desc.Hin, desc.Win, desc.Cout, desc.k, desc.pad, st), "tap_unfold")
             if ctx.needs_input_grad[0]:
                 gx = torch.empty_like(x)
-                L.check(_timed(_conv_tag("dgrad", desc1), _conv_flops(desc1), lambda: lib.sgk_conv_dgrad(
+                L.check(_timed(_conv_tag("dgrad", desc1), _conv_flops(desc1), _conv_bytes(desc1), lambda st: lib.sgk_conv_dgrad(
                     ctypes.byref(desc1), _p(g32), _p(wpd), _p(gx), st)), "conv_dgrad(tap 1x1)")
             if ctx.needs_input_grad[1]:
                 gw = torch.empty_like(weight)
                 dw32 = torch.empty((32, desc.Cin), dtype=torch.float32, device=dy.device)
                 ws = _ws(lib.sgk_conv_wgrad_workspace_bytes(ctypes.byref(desc1)), dy.device)
-                L.check(_timed(_conv_tag("wgrad", desc1), _conv_flops(desc1), lambda: lib.sgk_conv_wgrad(
+                L.check(_timed(_conv_tag("wgrad", desc1), _conv_flops(desc1), _conv_bytes(desc1), lambda st: lib.sgk_conv_wgrad(
                     ctypes.byref(desc1), _p(x), _p(g32), _p(dw32), None, _p(ws), ws.numel(), st)), "conv_wgrad(tap 1x1)")
                 L.check(lib.sgk_tap_weight_unpack(_p(dw32), _p(gw), desc.Cout, desc.Cin, desc.k, st), "tap_weight_unpack")
             if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -386,7 +428,7 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dy.device)
             wp = cfg.packed(weight, desc, L.OP_DGRAD)
-            L.check(_timed(_conv_tag("dgrad", bdesc), _conv_flops(desc), lambda: lib.sgk_conv_dgrad(
+            L.check(_timed(_conv_tag("dgrad", bdesc), _conv_flops(desc), _conv_bytes(desc), lambda st: lib.sgk_conv_dgrad(
                 ctypes.byref(bdesc), _p(dy), _p(wp), _p(gx), st)), "conv_dgrad")
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if want_b and ctx.bias_grad_zero:
@@ -399,7 +441,7 @@ class _ConvFn(torch.autograd.Function):
             wdesc = ctx.descp if ctx.descp is not None else bdesc
             nbytes = lib.sgk_conv_wgrad_workspace_bytes(ctypes.byref(wdesc))
             ws = _ws(nbytes, dy.device)
-            L.check(_timed(_conv_tag("wgrad", wdesc), _conv_flops(wdesc), lambda: lib.sgk_conv_wgrad(
+            L.check(_timed(_conv_tag("wgrad", wdesc), _conv_flops(wdesc), _conv_bytes(wdesc), lambda st: lib.sgk_conv_wgrad(
                 ctypes.byref(wdesc), _p(x), _p(dy), _p(gw), _p(gb) if want_b else None, _p(ws), ws.numel(), st)), "conv_wgrad")
         elif want_b:
             gb = torch.empty(desc.Cout, dtype=torch.float32, device=dy.device)
@@ -426,8 +468,10 @@ class _NormActFn(torch.autograd.Function):
         y = torch.empty_like(x)
         stats = torch.empty(groups * C * 2, dtype=torch.float32, device=x.device)
         ws = _ws(lib.sgk_norm_workspace_bytes(N, C, H, W), x.device)
-        L.check(lib.sgk_norm_act_fwd(_p(x), _p(y), _p(stats), _p(g), _p(b), _p(running_mean), _p(running_var), momentum, eps,
-                                     N, C, H, W, int(per_sample), act, slope, _p(ws), ws.numel(), _stream()), "norm_act_fwd")
+        L.check(_timed("norm_fwd %s C%d %dx%d N%d" % ("IN" if per_sample else "BN", C, H, W, N), 0.0, 8.0 * x.numel(),
+                       lambda st: lib.sgk_norm_act_fwd(_p(x), _p(y), _p(stats), _p(g), _p(b), _p(running_mean), _p(running_var),
+                                                       momentum, eps, N, C, H, W, int(per_sample), act, slope, _p(ws),
+                                                       ws.numel(), st)), "norm_act_fwd")
         ctx.args = (per_sample, act, slope, gamma is not None)
         ctx.save_for_backward(x, stats, g, b)
         return y
@@ -443,8 +487,9 @@ class _NormActFn(torch.autograd.Function):
         dg = torch.empty(C, dtype=torch.float32, device=x.device) if affine else None
         db = torch.empty(C, dtype=torch.float32, device=x.device) if affine else None
         ws = _ws(lib.sgk_norm_workspace_bytes(N, C, H, W), x.device)
-        L.check(lib.sgk_norm_act_bwd(_p(dy), _p(x), _p(stats), _p(g), _p(b), _p(dx), _p(dg), _p(db), N, C, H, W,
-                                     int(per_sample), act, slope, _p(ws), ws.numel(), _stream()), "norm_act_bwd")
+        L.check(_timed("norm_bwd %s C%d %dx%d N%d" % ("IN" if per_sample else "BN", C, H, W, N), 0.0, 12.0 * x.numel(),
+                       lambda st: lib.sgk_norm_act_bwd(_p(dy), _p(x), _p(stats), _p(g), _p(b), _p(dx), _p(dg), _p(db), N, C, H, W,
+                                                       int(per_sample), act, slope, _p(ws), ws.numel(), st)), "norm_act_bwd")
         return dx, dg, db, None, None, None, None, None, None, None
 
 
@@ -463,7 +508,8 @@ class _ToNHWC(torch.autograd.Function):
         x = _chk(x, "input")
         N, C, H, W = x.shape
         y = torch.empty((N, H, W, C), dtype=torch.float32, device=x.device)
-        L.check(L.load().sgk_layout_nchw_to_nhwc(_p(x), _p(y), N, C, H, W, _stream()), "nchw_to_nhwc")
+        L.check(_timed("nchw_to_nhwc C%d %dx%d N%d" % (C, H, W, N), 0.0, 8.0 * x.numel(),
+                       lambda st: L.load().sgk_layout_nchw_to_nhwc(_p(x), _p(y), N, C, H, W, st)), "nchw_to_nhwc")
         return y
 
     @staticmethod
@@ -623,7 +669,8 @@ class _GaussDecimate(torch.autograd.Function):
         N, H, W, C = x.shape
         Ho, Wo = (H + scale - 1) // scale, (W + scale - 1) // scale
         y = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=x.device)
-        L.check(L.load().sgk_gauss_decimate_fwd(_p(x), _p(taps), _p(y), N, C, H, W, k, scale, _stream()), "gauss_fwd")
+        L.check(_timed("gauss_fwd k%d s%d C%d %dx%d N%d" % (k, scale, C, H, W, N), 0.0, 4.0 * (x.numel() + y.numel()),
+                       lambda st: L.load().sgk_gauss_decimate_fwd(_p(x), _p(taps), _p(y), N, C, H, W, k, scale, st)), "gauss_fwd")
         ctx.args = (x.shape, k, scale)
         ctx.save_for_backward(taps)
         return y
@@ -637,7 +684,8 @@ class _GaussDecimate(torch.autograd.Function):
         dy = _chk(dy, "grad")
         N, H, W, C = shape
         dx = torch.empty(shape, dtype=torch.float32, device=dy.device)
-        L.check(L.load().sgk_gauss_decimate_bwd(_p(dy), _p(taps), _p(dx), N, C, H, W, k, scale, _stream()), "gauss_bwd")
+        L.check(_timed("gauss_bwd k%d s%d C%d %dx%d N%d" % (k, scale, C, H, W, N), 0.0, 4.0 * (dx.numel() + dy.numel()),
+                       lambda st: L.load().sgk_gauss_decimate_bwd(_p(dy), _p(taps), _p(dx), N, C, H, W, k, scale, st)), "gauss_bwd")
         return dx, None, None, None
 
 

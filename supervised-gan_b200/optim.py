@@ -49,10 +49,9 @@ class FusedAdam(torch.optim.Optimizer):
         lib = L.load()
         if not torch.cuda.is_current_stream_capturing():
             self.sync_hyper()
-        stream = torch.cuda.current_stream().cuda_stream
         for gi, group in enumerate(self.param_groups):
             st = self._group_state(gi, group)
-            entries = []
+            entries, keep = [], []
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -71,14 +70,17 @@ class FusedAdam(torch.optim.Optimizer):
                     s["step"] = st["step"]
                 # the launch below is stream-ordered and the caching allocator is stream-safe: the gradient needs no
                 # extra reference (one kept in `state` would be serialised by state_dict() and double gradient memory)
+                keep.append(g)
                 entries.append((p.data_ptr(), g.data_ptr(), s["exp_avg"].data_ptr(), s["exp_avg_sq"].data_ptr(), p.numel()))
             if not entries:
                 continue
             arr = (L.SgkAdamTensor * len(entries))()
             for i, e in enumerate(entries):
                 arr[i].p, arr[i].g, arr[i].m, arr[i].v, arr[i].n = e
-            L.check(lib.sgk_adam_multi_tensor(arr, len(entries), st["step"].data_ptr(), st["hyper"].data_ptr(), stream),
-                    "adam_multi_tensor")
+            nparam = sum(e[4] for e in entries)
+            L.check(ops._timed("adam %d tensors %d params" % (len(entries), nparam), 0.0, 28.0 * nparam,
+                               lambda s_, arr=arr, n=len(entries), st=st, keep=keep: lib.sgk_adam_multi_tensor(
+                                   arr, n, st["step"].data_ptr(), st["hyper"].data_ptr(), s_)), "adam_multi_tensor")
         ops.bump_weights_epoch([p for group in self.param_groups for p in group["params"]])
         return None
 

@@ -220,7 +220,7 @@ class TwoStageCycleModel(BaseModel):
                 + self.loss_G2_fake_cycle * o.lambda_A_cycle * o.lambda_fake_cycle
             self.loss_G.backward()
 
-    def optimize_parameters(self):
+    def _optimize_parameters_eager(self):
         self.forward()
         for _ in range(self.opt.n_update_D1):
             self.optimizer_D1.zero_grad(set_to_none=True)

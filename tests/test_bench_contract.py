@@ -1,5 +1,6 @@
-"""bench.py contract on CPU: the reference arm (the oracle port on host cores) must print ONE JSON line with the keys the
-driver reads, on the same metric / unit / workload string as the GPU arm."""
+"""bench.py contract on CPU: the reference arm (the unmodified reference FCGANModel from baseline/_ref or /root/reference on
+the host cores, else the oracle port) must print ONE JSON line with the keys the driver reads, on the same metric / unit /
+config as the GPU arm, using every host core even when torchrun exported OMP_NUM_THREADS=1."""
 import json
 import os
 import subprocess
@@ -9,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_contract_line():
-    env = dict(os.environ, OMP_NUM_THREADS=os.environ.get("OMP_NUM_THREADS", "8"))
+    env = dict(os.environ, OMP_NUM_THREADS="1")      # what torchrun exports: the arm must override it
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
                           "--batch", "1"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -17,10 +18,13 @@ def test_reference_arm_prints_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     import bench
-    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT
-    assert d["config"]["workload"] == bench.WORKLOAD
+    import argparse
+    assert d["impl"] == "reference" and d["metric"] == bench.WORKLOADS["fcgan"]["metric"] and d["unit"] == bench.UNIT
+    assert d["config"] == bench.line_config(argparse.Namespace(config="fcgan", pool_size=50, batch=1), 1)   # what our arm prints
     assert d["higher_is_better"] is True and d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_loader
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
