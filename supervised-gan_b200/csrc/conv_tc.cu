@@ -1020,6 +1020,9 @@ conv_window_persist_kernel(const __grid_constant__ ImPParams p, const __grid_con
   if (warp == 1) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
 }
 
+int conv_patch_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, const float* w, const float* bias, float* out,
+                  int act, float slope, cudaStream_t st);   // conv_patch.cu
+
 static int pick_bn(int Co) {
   for (int bn : {256, 128, 64, 32})
     if (Co % bn == 0) return bn;
@@ -1029,6 +1032,11 @@ static int pick_bn(int Co) {
 int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, const float* w, const float* bias, float* out,
                 int act, float slope, cudaStream_t st) {
   if (d->precision != SGK_TF32) return SGK_EUNSUPPORTED;  // bf16 operands: not built yet
+  // patch-reuse kernel (conv_patch.cu): stride-2 / sub-pixel layers and the 1-2 channel image outputs
+  {
+    const int prc = conv_patch_tc(d, g, in, w, bias, out, act, slope, st);
+    if (prc != SGK_EUNSUPPORTED) return prc;
+  }
   // Thin-channel problems (Cin < 32 or Cout <= 16) are HBM/issue-bound; measured on B200 the CUDA-core thin kernels
   // beat the tensor-core tile for them (profiles/), so they are only routed here when SGK_TC_THIN=1.
   static const bool tc_thin = getenv("SGK_TC_THIN") != nullptr && atoi(getenv("SGK_TC_THIN")) != 0;

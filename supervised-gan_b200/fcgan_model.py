@@ -245,9 +245,11 @@ class FCGANModel(object):
         # (update_learning_rate) before replaying -- a tuple compare, and one small H2D copy only when something changed
         self.optimizer_D.sync_hyper()
         self.optimizer_G.sync_hyper()
-        self.fake_pool.prepare_replay()          # this step's pool decisions (Python `random`, the reference's order)
         g_fwd.replay()
         self._wait_input()
+        # This step's pool decisions (Python `random`, the reference's order).  AFTER the first graph: the plan buffers were
+        # allocated while capturing g_upd from the pool both graphs share, where they may alias temporaries of g_fwd.
+        self.fake_pool.prepare_replay()
         g_upd.replay()
         ops.bump_weights_epoch()
 

@@ -43,8 +43,8 @@ class ImagePool():
                     plan.append(-1)
         return plan
 
-    def _upload(self, slot, plan):
-        if plan != slot[1]:
+    def _upload(self, slot, plan, force=False):
+        if force or plan != slot[1]:
             # pageable source: the driver stages the 4*B bytes before returning, so the host list may change right away
             slot[0].copy_(torch.tensor(plan, dtype=torch.int32))
             slot[1] = plan
@@ -53,7 +53,10 @@ class ImagePool():
         """Before replaying a CUDA graph that contains this pool's queries: draws the decisions of every captured query,
         in capture order, and writes them into the plan buffers the captured kernels read."""
         for slot in self._graph_plans:
-            self._upload(slot, self._draw(slot[0].numel()))
+            # always rewritten: a buffer allocated while capturing lives in the graph's memory pool, where another graph
+            # sharing that pool (the step drivers capture the generator forward separately) may use the same bytes as a
+            # temporary -- call this AFTER such graphs have replayed and right before the one holding the query
+            self._upload(slot, self._draw(slot[0].numel()), force=True)
 
     # ------------------------------------------------------------------ device side
     def query(self, images, out=None):
