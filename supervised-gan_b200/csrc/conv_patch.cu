@@ -23,12 +23,13 @@
 #include "conv_plan.h"
 #include <cuda.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 #include "tc_ptx.cuh"
 
 namespace sgk {
 
-constexpr int PT_THREADS = 256;
+constexpr int PT_THREADS = 384;     // warps 0-2 producers / MMA issuer, 3 idle, 4-11 two epilogue groups
 constexpr int PT_MAXJOBS = 16;
 constexpr int PT_TW = 8;              // tile width in pixels: one 8-row swizzle group of the A operand = 8 pixels of a patch row
 
@@ -73,7 +74,9 @@ struct PatchParams {
   int acc_stride;                     // columns per accumulator SET (mt * acc_cols)
   int nsets;                          // accumulator sets in flight (the role hand-offs cost ~1 us: the tile rate is nsets per round trip)
   int spin;                           // experiments: 1 = mbarrier.test_wait spin loops instead of try_wait
+  int dbg;                            // ablation bits (SGK_PATCH_DBG): 1 no stores, 2 one MMA per job, 4 no TMA, 8 no epilogue body, 16 no MMAs
   int tmem_cols;
+  long long* trace;                    // development: clock64 stamps of CTA 0 (SGK_PATCH_TRACE=1)
 };
 
 struct alignas(64) PatchMaps {
@@ -108,18 +111,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int NPL, int JPP, bool RW>
 __global__ void __launch_bounds__(PT_THREADS, 1)
 conv_patch_tc_kernel(const __grid_constant__ PatchParams p, const __grid_constant__ PatchMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
+  const int lane = threadIdx.x & 31;
   const int SA = p.sa, SB = p.sb;
   const uint32_t a_ring = smem_base;
   const uint32_t w_base = a_ring + (uint32_t)SA * p.plane_bytes;                       // resident weights or the weight ring
   const uint32_t w_bytes = p.rw ? (uint32_t)(p.nchunks * p.njobs) * p.job_tile_bytes : (uint32_t)SB * p.job_tile_bytes;
   const uint32_t stg_base = w_base + w_bytes;                                          // epilogue transpose: 4 warps x 32 rows x 128 B
-  const uint32_t bar_base = stg_base + (p.thin ? 0u : 16384u);
+  const uint32_t bar_base = stg_base + (p.thin ? 0u : 32768u);
   auto afull = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto aempty = [&](int s) { return bar_base + 8u * (uint32_t)(SA + s); };
   auto bfull = [&](int s) { return bar_base + 8u * (uint32_t)(2 * SA + s); };
@@ -128,28 +139,24 @@ conv_patch_tc_kernel(const __grid_constant__ PatchParams p, const __grid_constan
   auto tfull = [&](int a) { return bar_base + 8u * (uint32_t)(2 * SA + 2 * SB + a); };
   auto tempty = [&](int a) { return bar_base + 8u * (uint32_t)(2 * SA + 2 * SB + NS + a); };
   const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * SA + 2 * SB + 2 * NS);
-  const bool spin = p.spin != 0;
-  auto wait = [&](uint32_t bar, uint32_t parity) {
-    if (spin) {
-      uint32_t ok = 0;
-      while (!ok)
-        asm volatile("{\n.reg .pred q;\nmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } else {
-      mbar_wait(bar, parity);
-    }
-  };
+  auto wait = [&](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
   const int n0 = blockIdx.y * p.BN;
   const int per_img = p.tiles_x * p.tiles_y;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (tr && threadIdx.x == 0) p.trace[0] = clock64();
+  const uint32_t wfull = tmem_slot + 8u;            // resident weights have landed (TMA mode)
+  const bool rw_tma = p.rw && !p.thin;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int a = 0; a < NS; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+    for (int a = 0; a < NS; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
+    mbar_init(wfull, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  if (p.rw) {
-    // resident weights: every job's B tile for every chunk, written in the K-major SWIZZLE_128B image (row r at r * 128,
+  if (p.rw && !rw_tma) {
+    // thin outputs: the few weight rows of every job / chunk, written in the K-major SWIZZLE_128B image (row r at r * 128,
     // 16-byte chunk j at j ^ (r & 7)); rows no sub-tile covers (phases that do not use the job's shift) stay zero
     float* wgen = reinterpret_cast<float*>(smem_gen + (w_base - smem_base));
     const int tile_f = (int)(p.job_tile_bytes >> 2);
@@ -177,108 +184,184 @@ conv_patch_tc_kernel(const __grid_constant__ PatchParams p, const __grid_constan
   tc_fence_after();
   uint32_t tmem_acc;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+  if (tr && threadIdx.x == 0) p.trace[1] = clock64();
 
+  // Roles 0-2 run with WARP-UNIFORM control flow (all 32 lanes walk the loops and wait on the barriers; one elected lane issues
+  // the TMA / tcgen05 instructions): loop counters, job-table reads and descriptors then live on the uniform datapath, which
+  // the single-lane form did not allow (measured ~240 clk per MMA issued, against ~70 clk of tensor time for N = 64).
+  const int ntiles = (int)p.total_tiles;
   if (warp == 0) {
     // =============================================================== patch producer
-    if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(p.PW * p.PH) * 128u;
-      int g = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int n = (int)(t / per_img);
-        const int r2 = (int)(t - (long long)n * per_img);
-        const int ty0 = (r2 / p.tiles_x) * (p.th * p.mt), tx0 = (r2 % p.tiles_x) * PT_TW;
-        for (int c = 0; c < p.nchunks; ++c)
-          for (int pl = 0; pl < p.nplanes; ++pl, ++g) {
-            const int s = g % SA;
-            wait(aempty(s), (uint32_t)(((g / SA) & 1) ^ 1));
-            mbar_arrive_expect_tx(afull(s), tx_bytes);
-            tma_load_4d_p(a_ring + (uint32_t)s * p.plane_bytes, &maps.a, c * 32, tx0 * p.is + p.px0[pl], ty0 * p.is + p.py0[pl], n,
-                          afull(s));
+    const bool leader = elect_one();
+    const uint32_t tx_bytes = (uint32_t)(p.PW * p.PH) * 128u;
+    int s = 0;
+    uint32_t ph = 1;                                  // ring slot and the parity to wait for on its `empty` barrier
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int n = t / per_img;
+      const int r2 = t - n * per_img;
+      const int ty0 = (r2 / p.tiles_x) * (p.th * p.mt), tx0 = (r2 % p.tiles_x) * PT_TW;
+      for (int c = 0; c < p.nchunks; ++c)
+        for (int pl = 0; pl < p.nplanes; ++pl) {
+          wait(aempty(s), ph);
+          if (leader) {
+            if (p.dbg & 4) {
+              mbar_arrive(afull(s));
+            } else {
+              mbar_arrive_expect_tx(afull(s), tx_bytes);
+              tma_load_4d_p(a_ring + (uint32_t)s * p.plane_bytes, &maps.a, c * 32, tx0 * p.is + p.px0[pl], ty0 * p.is + p.py0[pl], n,
+                            afull(s));
+            }
           }
-      }
+          if (++s == SA) { s = 0; ph ^= 1u; }
+        }
+      if (tr && leader) { const int ti = (t - (int)blockIdx.x) / (int)gridDim.x; if (ti < 32) p.trace[8 + ti * 4] = clock64(); }
     }
   } else if (warp == 2) {
-    // =============================================================== weight producer (streaming mode)
-    if (lane == 0 && !p.rw) {
-      int g = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x)
+    // =============================================================== weight producer
+    const bool leader = elect_one();
+    if (rw_tma) {
+      // resident weights: every (chunk, job) B tile once, straight into its K-major SWIZZLE_128B image
+      if (leader) {
+        uint32_t bytes = 0;
+        for (int j = 0; j < p.njobs; ++j) bytes += (uint32_t)(p.jobs[j].nsub * p.jobs[j].sub_rows) * 128u;
+        mbar_arrive_expect_tx(wfull, bytes * (uint32_t)p.nchunks);
         for (int c = 0; c < p.nchunks; ++c)
-          for (int j = 0; j < p.njobs; ++j, ++g) {
-            const PatchJob& J = p.jobs[j];
-            const int s = g % SB;
-            wait(bempty(s), (uint32_t)(((g / SB) & 1) ^ 1));
-            mbar_arrive_expect_tx(bfull(s), (uint32_t)(J.nsub * J.sub_rows) * 128u);
-            const uint32_t dst = w_base + (uint32_t)s * p.job_tile_bytes;
-            for (int q = 0; q < J.nsub; ++q)
-              tma_load_2d(dst + (uint32_t)J.row_off[q] * 128u, &maps.w[J.wmap[q]], J.wcol[q] + c * 32, n0, bfull(s));
+          for (int j = 0; j < p.njobs; ++j) {
+            const uint32_t dst = w_base + (uint32_t)(c * p.njobs + j) * p.job_tile_bytes;
+            for (int q = 0; q < p.jobs[j].nsub; ++q)
+              tma_load_2d(dst + (uint32_t)p.jobs[j].row_off[q] * 128u, &maps.w[p.jobs[j].wmap[q]], p.jobs[j].wcol[q] + c * 32, n0, wfull);
+          }
+      }
+    } else if (!RW) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+        for (int c = 0; c < p.nchunks; ++c)
+          for (int j = 0; j < p.njobs; ++j) {
+            wait(bempty(s), ph);
+            if (leader) {
+              mbar_arrive_expect_tx(bfull(s), (uint32_t)(p.jobs[j].nsub * p.jobs[j].sub_rows) * 128u);
+              const uint32_t dst = w_base + (uint32_t)s * p.job_tile_bytes;
+              for (int q = 0; q < p.jobs[j].nsub; ++q)
+                tma_load_2d(dst + (uint32_t)p.jobs[j].row_off[q] * 128u, &maps.w[p.jobs[j].wmap[q]], p.jobs[j].wcol[q] + c * 32, n0, bfull(s));
+            }
+            if (++s == SB) { s = 0; ph ^= 1u; }
           }
     }
   } else if (warp == 1) {
     // =============================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t sbo = (uint32_t)p.PW * 128u;
-      int ga = 0, gb = 0, it = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const int ab = it % NS;
-        wait(tempty(ab), (uint32_t)(((it / NS) & 1) ^ 1));   // the epilogue has drained this accumulator set
-        tc_fence_after();
-        const uint32_t acc0 = tmem_acc + (uint32_t)(ab * p.acc_stride);
-        bool first = true;
-        for (int c = 0; c < p.nchunks; ++c) {
-          int j = 0;
-          for (int pl = 0; pl < p.nplanes; ++pl, ++ga) {
-            const int s = ga % SA;
-            wait(afull(s), (uint32_t)((ga / SA) & 1));
-            tc_fence_after();
-            const uint32_t plane = a_ring + (uint32_t)s * p.plane_bytes;
-            for (; j < p.njobs && p.jobs[j].plane == pl; ++j) {
-              const PatchJob& J = p.jobs[j];
-              uint32_t btile;
-              if (p.rw) {
-                btile = w_base + (uint32_t)(c * p.njobs + j) * p.job_tile_bytes;
-              } else {
-                const int sbi = gb % SB;
-                wait(bfull(sbi), (uint32_t)((gb / SB) & 1));
-                tc_fence_after();
-                btile = w_base + (uint32_t)sbi * p.job_tile_bytes;
-              }
-              const uint32_t idesc = make_idesc_tf32(128, J.N);
-              for (int q = 0; q < p.mt; ++q) {
-                const uint32_t arow = plane + (uint32_t)(J.shift + q * p.th * p.PW) * 128u;
-                const uint32_t dcol = acc0 + (uint32_t)(q * p.acc_cols + J.acc_col);
+    // A lone warp issues roughly one dependent instruction every 4-6 clocks, so this loop is written for instruction count:
+    // ring positions are (slot, parity) counters, descriptors are (constant high word, 16-byte-unit low word) pairs, and with
+    // a compile-time job-table shape every PatchJob field is a constant-bank operand.
+    const bool leader = elect_one();
+    // K-major SWIZZLE_128B descriptors: high word = SBO >> 4 | version 1 << 14 | layout 2 << 29, low word = addr >> 4 | LBO 1 << 16
+    const uint32_t ahi = (((uint32_t)p.PW * 128u) >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t bhi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t aring_lo = (a_ring >> 4) | (1u << 16), wbase_lo = (w_base >> 4) | (1u << 16);
+    const uint32_t plane_units = p.plane_bytes >> 4, jt_units = p.job_tile_bytes >> 4, q_units = (uint32_t)(p.th * p.PW) * 8u;
+    const int nk = (p.dbg & 16) ? 0 : ((p.dbg & 2) ? 1 : 4);
+    int sa_i = 0, sb_i = 0, ab = 0, it = 0;
+    uint32_t sa_ph = 0, sb_ph = 0, ab_ph = 1;
+    uint32_t plane_lo = aring_lo, bring_lo = wbase_lo;
+    if (rw_tma) { wait(wfull, 0u); tc_fence_after(); }
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      wait(tempty(ab), ab_ph);                          // the epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t acc0 = tmem_acc + (uint32_t)(ab * p.acc_stride);
+      uint32_t accum = 0;
+      auto job = [&](const PatchJob& J, uint32_t blo_resident) {
+        uint32_t blo = blo_resident;
+        if (!RW) {
+          wait(bfull(sb_i), sb_ph);
+          tc_fence_after();
+          blo = bring_lo;
+        }
+        const uint32_t idesc = make_idesc_tf32(128, J.N);
+        uint32_t alo = plane_lo + (uint32_t)J.shift * 8u;
+        uint32_t dcol = acc0 + (uint32_t)J.acc_col;
+        if (leader) {
+#pragma unroll 1
+          for (int q = 0; q < p.mt; ++q, alo += q_units, dcol += (uint32_t)p.acc_cols) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma_tf32(dcol, make_sw128_kmajor_desc_sbo(arow + kk * 32, sbo), make_sw128_kmajor_desc(btile + kk * 32), idesc,
-                            (uint32_t)((first && kk == 0) ? 0 : 1));
-              }
-              first = false;
-              if (!p.rw) { umma_commit(bempty(gb % SB)); ++gb; }
-            }
-            umma_commit(aempty(s));
+            for (int kk = 0; kk < 4; ++kk)
+              if (kk < nk)
+                umma_tf32(dcol, ((uint64_t)ahi << 32) | (uint64_t)(alo + 2u * kk), ((uint64_t)bhi << 32) | (uint64_t)(blo + 2u * kk), idesc,
+                          kk == 0 ? accum : 1u);
+          }
+          if (!RW) umma_commit(bempty(sb_i));
+        }
+        accum = 1;
+        if (!RW) {
+          bring_lo += jt_units;
+          if (++sb_i == SB) { sb_i = 0; sb_ph ^= 1u; bring_lo = wbase_lo; }
+        }
+      };
+      uint32_t wres_lo = wbase_lo;                      // resident weights: tile of (chunk, job), walked in issue order
+      for (int c = 0; c < p.nchunks; ++c) {
+        if constexpr (NPL > 0) {
+#pragma unroll
+          for (int pl = 0; pl < NPL; ++pl) {
+            wait(afull(sa_i), sa_ph);
+            tc_fence_after();
+#pragma unroll
+            for (int jj = 0; jj < JPP; ++jj) { job(p.jobs[pl * JPP + jj], wres_lo); wres_lo += jt_units; }
+            if (leader) umma_commit(aempty(sa_i));
+            plane_lo += plane_units;
+            if (++sa_i == SA) { sa_i = 0; sa_ph ^= 1u; plane_lo = aring_lo; }
+          }
+        } else {
+          int j = 0;
+          for (int pl = 0; pl < p.nplanes; ++pl) {
+            wait(afull(sa_i), sa_ph);
+            tc_fence_after();
+            for (; j < p.njobs && p.jobs[j].plane == pl; ++j) { job(p.jobs[j], wres_lo); wres_lo += jt_units; }
+            if (leader) umma_commit(aempty(sa_i));
+            plane_lo += plane_units;
+            if (++sa_i == SA) { sa_i = 0; sa_ph ^= 1u; plane_lo = aring_lo; }
           }
         }
-        umma_commit(tfull(ab));
       }
+      if (leader) {
+        umma_commit(tfull(ab));
+        if (tr && it < 32) p.trace[8 + it * 4 + 1] = clock64();
+      }
+      if (++ab == NS) { ab = 0; ab_ph ^= 1u; }
     }
   } else if (warp >= 4) {
     // =============================================================== epilogue
-    const int ew = warp - 4;
+    // two groups of four warps (a warp reads the TMEM lane quarter warp % 4): group eg takes every second 32-column block of
+    // a tile, so that two warps per scheduler hide each other's tcgen05.ld / shared-memory latencies
+    const int eg = (warp - 4) >> 2, ew = (warp - 4) & 3;
     const int r_own = ew * 32 + lane;                 // tile row == TMEM lane of this thread: pixel (r >> 3, r & 7)
     const uint32_t lane_base = tmem_acc + ((uint32_t)(ew * 32) << 16);
     const bool simple = p.act == SGK_ACT_NONE || p.act == SGK_ACT_RELU || p.act == SGK_ACT_LRELU;
     const float sl = p.act == SGK_ACT_NONE ? 1.f : (p.act == SGK_ACT_RELU ? 0.f : p.slope);
     const uint32_t j8 = (uint32_t)(lane & 7);
     const int rsub = lane >> 3;
-    const uint32_t stg = stg_base + (uint32_t)ew * 4096u;
-    int it = 0;
-    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const int ab = it % NS;
-      const int n = (int)(t / per_img);
-      const int r2 = (int)(t - (long long)n * per_img);
+    const uint32_t stg = stg_base + (uint32_t)(eg * 4 + ew) * 4096u;
+    int it = 0, ab = -1;
+    uint32_t ab_ph = 1;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      if (++ab == NS || it == 0) { ab = 0; ab_ph ^= 1u; }
+      const int n = t / per_img;
+      const int r2 = t - n * per_img;
       const int ty0 = (r2 / p.tiles_x) * (p.th * p.mt), tx0 = (r2 % p.tiles_x) * PT_TW;
-      wait(tfull(ab), (uint32_t)((it / NS) & 1));
+      wait(tfull(ab), ab_ph);
       tc_fence_after();
+      if (tr && threadIdx.x == 128 && it < 32) p.trace[8 + it * 4 + 2] = clock64();
+      if (tr && threadIdx.x == 128 && it > 0 && it <= 32) p.trace[8 + (it - 1) * 4 + 3] = p.trace[8 + it * 4 + 2];
       const uint32_t set_addr = lane_base + (uint32_t)(ab * p.acc_stride);
+      if (p.dbg & 8) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(ab));
+        continue;
+      }
+      if (p.thin && eg == 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(ab));
+        continue;
+      }
       if (p.thin) {
         // nacc phases x Co (<= 2) channels in the first columns of a 16-column block: each thread owns one pixel of the phase
         // grid and writes its os x os output pixels directly (8 neighbouring lanes = 8 neighbouring x: contiguous runs)
@@ -310,14 +393,19 @@ conv_patch_tc_kernel(const __grid_constant__ PatchParams p, const __grid_constan
       } else {
         const int nchunk32 = p.BN >> 5;
         const int nblk = p.mt * p.nacc * nchunk32;
-        for (int blk = 0; blk < nblk; ++blk) {
+        const int last_blk = nblk - 1 - ((nblk - 1 - eg) & 1);      // this group's last block (< eg: none)
+        if (last_blk < eg) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(ab));
+        }
+        for (int blk = eg; blk < nblk; blk += 2) {
           const int q = blk / (p.nacc * nchunk32);
           const int rem = blk - q * p.nacc * nchunk32;
           const int f = rem / nchunk32, cc = (rem - f * nchunk32) << 5;
           uint32_t v[32];
           tmem_ld32(set_addr + (uint32_t)(q * p.acc_cols + f * p.BN + cc), v);
           tmem_ld_wait();
-          if (blk == nblk - 1) {
+          if (blk == last_blk) {
             // the whole accumulator set is in registers / written out: hand it back to the MMA warp before the last stores
             tc_fence_before();
             __syncwarp();
@@ -331,7 +419,7 @@ conv_patch_tc_kernel(const __grid_constant__ PatchParams p, const __grid_constan
                          : "memory");
           __syncwarp();
           const float4 b4 = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cc + 4 * j8)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const int Hpf = p.Hp[f], Wpf = p.Wp[f];
+          const int Hpf = p.Hp[f], Wpf = p.Wp[f], ooyf = p.ooy[f], ooxf = p.oox[f];
           float* __restrict__ obase = p.out + (long long)n * p.Ho * p.Wo * p.Co + n0 + cc + 4 * j8;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -351,8 +439,8 @@ conv_patch_tc_kernel(const __grid_constant__ PatchParams p, const __grid_constan
               o.x = act_apply(o.x, p.act, p.slope); o.y = act_apply(o.y, p.act, p.slope);
               o.z = act_apply(o.z, p.act, p.slope); o.w = act_apply(o.w, p.act, p.slope);
             }
-            if (ry < p.th && y < Hpf && x < Wpf)
-              *reinterpret_cast<float4*>(obase + ((long long)(y * p.os + p.ooy[f]) * p.Wo + (x * p.os + p.oox[f])) * p.Co) = o;
+            if (ry < p.th && y < Hpf && x < Wpf && !(p.dbg & 1))
+              *reinterpret_cast<float4*>(obase + ((long long)(y * p.os + ooyf) * p.Wo + (x * p.os + ooxf)) * p.Co) = o;
           }
           __syncwarp();
         }
@@ -361,6 +449,7 @@ conv_patch_tc_kernel(const __grid_constant__ PatchParams p, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) p.trace[2] = clock64();
   if (warp == 1) tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
 }
 
@@ -387,13 +476,11 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-// Which layers take this kernel (SGK_PATCH: 0 = never, 1 = default policy, 2 = every eligible shape).
-// Default policy, from the per-layer measurements in profiles/: thin image outputs always; wide layers when the tile count
-// fills the machine and the layer is not the 256-wide stride-1 class that conv_tma_tc_kernel already runs at 75-85 %.
+// Launches the patch kernel if the shape is eligible (SGK_EUNSUPPORTED otherwise).  WHICH eligible layers use it is decided by
+// the caller, conv_fwd_tc (conv_tc.cu): thin image outputs always, everything else by a per-shape timing of both kernels.
 int conv_patch_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, const float* w, const float* bias, float* out,
                   int act, float slope, cudaStream_t st) {
-  static const int mode = env_int("SGK_PATCH", 1);
-  if (mode == 0 || d->precision != SGK_TF32) return SGK_EUNSUPPORTED;
+  if (d->precision != SGK_TF32) return SGK_EUNSUPPORTED;
   if ((g.Cg % 32) != 0 || g.nphase < 1) return SGK_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(in) & 15) != 0 || (reinterpret_cast<uintptr_t>(w) & 15) != 0) return SGK_EUNSUPPORTED;
   const bool thin = g.Co <= 2;
@@ -545,6 +632,7 @@ int conv_patch_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, co
   p.tiles_y = ceil_div(Hmax, p.th * mt);
   p.total_tiles = (long long)g.N * p.tiles_x * p.tiles_y;
   if (p.total_tiles == 0) return SGK_OK;
+  if (p.total_tiles > 0x3fffffffLL) return SGK_EUNSUPPORTED;
   p.acc_stride = mt * p.acc_cols;
   int nsets = 512 / p.acc_stride;
   if (nsets > 8) nsets = 8;
@@ -552,23 +640,16 @@ int conv_patch_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, co
   if (nsets < 2) return SGK_EUNSUPPORTED;
   p.nsets = nsets;
   p.spin = env_int("SGK_PATCH_SPIN", 0);
+  p.dbg = env_int("SGK_PATCH_DBG", 0);
   int tc = 32;
   while (tc < nsets * p.acc_stride) tc <<= 1;
   if (tc > 512) return SGK_EUNSUPPORTED;
   p.tmem_cols = tc;
   if (p.PW * is > 256 || p.PH * is > 256) return SGK_EUNSUPPORTED;
 
-  // ---- policy
-  if (mode == 1 && !thin) {
-    // measured (profiles/r2_patch_layers.md): pays for stride-2 / sub-pixel layers on grids that fill the machine; the
-    // stride-1 k4 layers (256-wide PatchGAN L4, 1x1 heads) stay on conv_tma_tc_kernel
-    const bool strided = g.transposed_type ? g.nphase == 4 : is == 2;
-    if (!strided || p.total_tiles * n_tiles_n < sm_count()) return SGK_EUNSUPPORTED;
-  }
-
   // ---- shared memory: patch ring + weights + epilogue staging + barriers
   const size_t w_bytes = p.rw ? rw_bytes : (size_t)p.sb * p.job_tile_bytes;
-  const size_t fixed = w_bytes + (thin ? 0 : 16384) + 8 * (2 * 8 + 2 * 4 + 2 * 8) + 16 + 1024;
+  const size_t fixed = w_bytes + (thin ? 0 : 32768) + 8 * (2 * 8 + 2 * 4 + 2 * 8) + 32 + 1024;
   int sa = env_int("SGK_PATCH_SA", thin ? 3 : 4);
   if (sa > 8) sa = 8;
   const size_t budget = 225 * 1024;
@@ -585,7 +666,7 @@ int conv_patch_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, co
   CUresult r = encode(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, adim, astr, abox, aest, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("conv_patch: cuTensorMapEncodeTiled(activations) failed (%d)", (int)r); return SGK_ECUDA; }
-  if (!p.rw) {
+  if (!thin) {
     for (int f = 0; f < g.nphase; ++f) {
       cuuint64_t gdim[2] = {(cuuint64_t)g.ph[f].kstride, (cuuint64_t)g.Co};
       cuuint64_t gstr[1] = {(cuuint64_t)g.ph[f].kstride * sizeof(float)};
@@ -597,11 +678,24 @@ int conv_patch_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, co
       if (r != CUDA_SUCCESS) { set_error("conv_patch: cuTensorMapEncodeTiled(weights) failed (%d)", (int)r); return SGK_ECUDA; }
     }
   }
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_patch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  // ---- kernel instantiation: compile-time job-table shape when every plane has the same number of jobs
+  int jpp = (njobs % p.nplanes) == 0 ? njobs / p.nplanes : 0;
+  for (int j = 0; j < njobs && jpp; ++j)
+    if (p.jobs[j].plane != j / jpp) jpp = 0;
+  if (env_int("SGK_PATCH_GENERIC", 0)) jpp = 0;
+  typedef void (*PatchKernel)(const PatchParams, const PatchMaps);
+  PatchKernel kern = p.rw ? conv_patch_tc_kernel<0, 0, true> : conv_patch_tc_kernel<0, 0, false>;
+  int kid = 0;
+  if (p.nplanes == 4 && jpp == 4) { kern = p.rw ? conv_patch_tc_kernel<4, 4, true> : conv_patch_tc_kernel<4, 4, false>; kid = 1; }
+  else if (p.nplanes == 1 && jpp == 4) { kern = p.rw ? conv_patch_tc_kernel<1, 4, true> : conv_patch_tc_kernel<1, 4, false>; kid = 2; }
+  else if (p.nplanes == 1 && jpp == 9) { kern = p.rw ? conv_patch_tc_kernel<1, 9, true> : conv_patch_tc_kernel<1, 9, false>; kid = 3; }
+  else if (p.nplanes == 1 && jpp == 16) { kern = p.rw ? conv_patch_tc_kernel<1, 16, true> : conv_patch_tc_kernel<1, 16, false>; kid = 4; }
+  kid = kid * 2 + (p.rw ? 1 : 0);
+  static bool attr[10] = {false, false, false, false, false, false, false, false, false, false};
+  if (!attr[kid]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_patch_tc_kernel)");
-    attr = true;
+    attr[kid] = true;
   }
   int per_sm = (int)(budget / smem);
   if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
@@ -611,7 +705,24 @@ int conv_patch_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, co
   if (gx < 1) gx = 1;
   if (gx > p.total_tiles) gx = p.total_tiles;
   dim3 grid((unsigned)gx, (unsigned)n_tiles_n);
-  conv_patch_tc_kernel<<<grid, PT_THREADS, smem, st>>>(p, maps);
+  static const int trace = env_int("SGK_PATCH_TRACE", 0);
+  if (trace) {
+    static long long* tbuf = nullptr;
+    if (!tbuf) cudaMalloc(&tbuf, 8 * 256);
+    cudaMemsetAsync(tbuf, 0, 8 * 256, st);
+    p.trace = tbuf;
+    kern<<<grid, PT_THREADS, smem, st>>>(p, maps);
+    cudaStreamSynchronize(st);
+    long long h[256];
+    cudaMemcpy(h, tbuf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[patch trace] grid %u x %u smem %zu tiles %lld th %d mt %d planes %d jobs %d chunks %d rw %d sa %d nsets %d BN %d | setup %lld total %lld clk\n",
+            grid.x, grid.y, smem, p.total_tiles, p.th, p.mt, p.nplanes, p.njobs, p.nchunks, p.rw, p.sa, p.nsets, p.BN, h[1] - h[0], h[2] - h[0]);
+    for (int i = 0; i < 32 && h[8 + i * 4 + 1]; ++i)
+      fprintf(stderr, "  tile %2d: tma issued %7lld  mma committed %7lld  epi start %7lld  epi next-start %7lld\n", i, h[8 + i * 4] - h[0],
+              h[8 + i * 4 + 1] - h[0], h[8 + i * 4 + 2] - h[0], h[8 + i * 4 + 3] - h[0]);
+    return SGK_OK;
+  }
+  kern<<<grid, PT_THREADS, smem, st>>>(p, maps);
   SGK_LAUNCH_CHECK("conv_patch_tc_kernel");
   return SGK_OK;
 }

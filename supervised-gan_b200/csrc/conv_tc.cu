@@ -31,6 +31,10 @@
 // smem so that every global store instruction writes 4 rows x 128 contiguous bytes of the NHWC output.
 #include "conv_plan.h"
 #include <cuda.h>
+#include <map>
+#include <mutex>
+#include <string.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "tc_ptx.cuh"
@@ -1029,14 +1033,95 @@ static int pick_bn(int Co) {
   return 0;
 }
 
+static int conv_fwd_tc_tile(const SgkConvDesc* d, const GatherPlan& g, const float* in, const float* w, const float* bias,
+                            float* out, int act, float slope, cudaStream_t st);
+
+// Kernel choice per problem shape.  conv_patch_tc_kernel (one input patch per tile, persistent) and conv_tma_tc_kernel (one
+// activation tile per tap, 3 CTAs per SM) win on different layers -- wave quantisation of the persistent tiles, N width and
+// stride all matter (profiles/r2_patch_layers.md) -- so the first eager call of a shape times both on the caller's stream
+// (CUDA events, best of 3) and the winner is cached for the process.  While a CUDA graph is being captured nothing can be
+// timed: an unseen shape then takes the static rule (strided / sub-pixel problems with <= 64 output channels -> patch).
+// SGK_PATCH: 0 = never patch, 1 = tuned (default), 2 = patch whenever eligible, 3 = static rule only.
+struct TuneKey {
+  int v[16];
+  bool operator<(const TuneKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+static std::mutex g_tune_mu;
+static std::map<TuneKey, int> g_tune;   // 1 = patch kernel, 0 = tile kernel
+
 int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, const float* w, const float* bias, float* out,
                 int act, float slope, cudaStream_t st) {
   if (d->precision != SGK_TF32) return SGK_EUNSUPPORTED;  // bf16 operands: not built yet
-  // patch-reuse kernel (conv_patch.cu): stride-2 / sub-pixel layers and the 1-2 channel image outputs
+  static const int mode = getenv("SGK_PATCH") ? atoi(getenv("SGK_PATCH")) : 1;
+  const bool thin_out = g.Co <= 2;
+  if (mode == 0) return conv_fwd_tc_tile(d, g, in, w, bias, out, act, slope, st);
+  if (mode == 2 || thin_out) {
+    const int prc = conv_patch_tc(d, g, in, w, bias, out, act, slope, st);
+    return prc != SGK_EUNSUPPORTED ? prc : conv_fwd_tc_tile(d, g, in, w, bias, out, act, slope, st);
+  }
+  const bool strided = g.transposed_type ? g.nphase == 4 : (g.nphase == 1 && g.ph[0].is == 2);
+  const int rule = strided && g.Co <= 64 ? 1 : 0;
+  TuneKey key{};
   {
+    const int kv[16] = {g.N, g.Hi, g.Wi, g.Cg, g.Ho, g.Wo, g.Co, g.k, g.transposed_type, g.nphase, g.ph[0].is, g.ph[0].ioy, g.ph[0].iox,
+                        g.ph[0].ta, g.ph[0].tb, bias != nullptr};
+    memcpy(key.v, kv, sizeof(kv));
+  }
+  int choice = -1;
+  {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    auto it = g_tune.find(key);
+    if (it != g_tune.end()) choice = it->second;
+  }
+  if (choice < 0) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (mode == 3 || cap != cudaStreamCaptureStatusNone) {
+      choice = rule;                                  // not cached: an eager call may still tune this shape later
+    } else {
+      // candidate 1 first: if the patch kernel does not take the shape there is nothing to tune
+      int rc = conv_patch_tc(d, g, in, w, bias, out, act, slope, st);
+      if (rc == SGK_EUNSUPPORTED) {
+        choice = 0;
+      } else {
+        if (rc != SGK_OK) return rc;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        float best[2] = {1e30f, 1e30f};
+        for (int cand = 1; cand >= 0 && rc == SGK_OK; --cand)
+          for (int rep = 0; rep < 4 && rc == SGK_OK; ++rep) {       // rep 0 warms up (tensor-map encode, first-launch costs)
+            cudaEventRecord(e0, st);
+            rc = cand ? conv_patch_tc(d, g, in, w, bias, out, act, slope, st) : conv_fwd_tc_tile(d, g, in, w, bias, out, act, slope, st);
+            cudaEventRecord(e1, st);
+            if (rc == SGK_EUNSUPPORTED && cand == 0) { rc = SGK_OK; best[0] = 1e30f; break; }
+            if (cudaEventSynchronize(e1) != cudaSuccess) { rc = SGK_ECUDA; break; }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best[cand]) best[cand] = ms;
+          }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (rc != SGK_OK) return rc;
+        choice = best[1] <= best[0] ? 1 : 0;
+        if (getenv("SGK_TUNE_LOG"))
+          fprintf(stderr, "[sgk tune] %s N%d %dx%dx%d -> %dx%dx%d k%d: patch %.1f us, tile %.1f us -> %s\n",
+                  g.transposed_type ? "sub-pixel" : "direct", g.N, g.Hi, g.Wi, g.Cg, g.Ho, g.Wo, g.Co, g.k, best[1] * 1e3f, best[0] * 1e3f,
+                  choice ? "patch" : "tile");
+      }
+      std::lock_guard<std::mutex> lk(g_tune_mu);
+      g_tune[key] = choice;
+    }
+  }
+  if (choice == 1) {
     const int prc = conv_patch_tc(d, g, in, w, bias, out, act, slope, st);
     if (prc != SGK_EUNSUPPORTED) return prc;
   }
+  return conv_fwd_tc_tile(d, g, in, w, bias, out, act, slope, st);
+}
+
+static int conv_fwd_tc_tile(const SgkConvDesc* d, const GatherPlan& g, const float* in, const float* w, const float* bias,
+                            float* out, int act, float slope, cudaStream_t st) {
   // Thin-channel problems (Cin < 32 or Cout <= 16) are HBM/issue-bound; measured on B200 the CUDA-core thin kernels
   // beat the tensor-core tile for them (profiles/), so they are only routed here when SGK_TC_THIN=1.
   static const bool tc_thin = getenv("SGK_TC_THIN") != nullptr && atoi(getenv("SGK_TC_THIN")) != 0;
