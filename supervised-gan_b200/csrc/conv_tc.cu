@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4)
 conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ TmaMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int S = p.stages;
   const int MT = p.mt;                                     // M tiles per CTA (1 or 2) sharing every weight k-block
   const uint32_t b_off = (uint32_t)MT * TC_A_BYTES;       // stage = MT activation tiles, then the weight tile
@@ -385,32 +385,42 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
   const int cchunks = p.Cg >> 5;
   const int KB = p.im2col ? 1 : P.ta * P.tb * cchunks;
 
-  // The TMA lane initialises the barriers itself and puts the first min(S, KB) stages in flight BEFORE the CTA-wide
+  // The TMA warp initialises the barriers itself and puts the first min(S, KB) stages in flight BEFORE the CTA-wide
   // sync, so the load latency of short tiles (1-8 k-blocks) overlaps the TMEM allocation and the barrier handshake.
+  // Producer and MMA warps run warp-uniform loops with one elected issuing lane and (slot, parity) ring counters: a lone
+  // warp retires about one dependent instruction per 4-6 clocks, so `% S`, `/ S` and per-MMA descriptor packing in these
+  // loops were a visible part of the k-block time on the narrow-N layers.
   const uint32_t tx_bytes = (uint32_t)nvalid * (uint32_t)(p.tw * p.th) * 128u + (uint32_t)p.BN * 128u;
-  int pa = 0, pb = 0, pc0 = 0, kb_issued = 0;
+  const bool leader = elect_one_lane();
+  int pa = 0, pb = 0, pc0 = 0, kb_issued = 0, ps = 0;
+  uint32_t pph = 1;                                       // parity to wait for on empty_bar(ps)
   auto issue_kb = [&](int kb) {
-    const int s = kb % S;
-    mbar_arrive_expect_tx(full_bar(s), tx_bytes);
-    const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
-    for (int q = 0; q < nvalid; ++q) {
-      if (p.im2col) tma_load_5d(abase + q * TC_A_BYTES, &maps.a, 0, txv[q], tyv[q], 0, tn[q], full_bar(s));
-      else tma_load_4d(abase + q * TC_A_BYTES, &maps.a, pc0, txv[q] * P.is + P.iox + pb, tyv[q] * P.is + P.ioy + pa, tn[q], full_bar(s));
+    if (leader) {
+      mbar_arrive_expect_tx(full_bar(ps), tx_bytes);
+      const uint32_t abase = smem_base + (uint32_t)ps * stage_bytes;
+      for (int q = 0; q < nvalid; ++q) {
+        if (p.im2col) tma_load_5d(abase + q * TC_A_BYTES, &maps.a, 0, txv[q], tyv[q], 0, tn[q], full_bar(ps));
+        else tma_load_4d(abase + q * TC_A_BYTES, &maps.a, pc0, txv[q] * P.is + P.iox + pb, tyv[q] * P.is + P.ioy + pa, tn[q], full_bar(ps));
+      }
+      tma_load_2d(abase + b_off, &maps.w[phi], kb * 32, n0, full_bar(ps));
     }
-    tma_load_2d(abase + b_off, &maps.w[phi], kb * 32, n0, full_bar(s));
     pc0 += 32;
     if (pc0 >= p.Cg) {
       pc0 = 0;
       if (++pb == P.tb) { pb = 0; ++pa; }
     }
+    if (++ps == S) { ps = 0; pph ^= 1u; }
   };
-  if (warp == 4 && lane == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);   // one arrive.expect_tx by the TMA thread (both boxes complete_tx on it)
-      mbar_init(empty_bar(s), 1);
+  if (warp == 4) {
+    if (leader) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(full_bar(s), 1);   // one arrive.expect_tx by the TMA thread (both boxes complete_tx on it)
+        mbar_init(empty_bar(s), 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
     }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
+    __syncwarp();
     const int first = KB < S ? KB : S;
     for (; kb_issued < first; ++kb_issued) issue_kb(kb_issued);
   }
@@ -490,33 +500,48 @@ conv_tma_tc_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ 
     }
   } else if (warp == 4) {
     // =============================================================== TMA producer (activations + weights)
-    if (lane == 0) {
-      for (int kb = kb_issued; kb < KB; ++kb) {
-        mbar_wait(empty_bar(kb % S), (uint32_t)(((kb / S) & 1) ^ 1));
-        issue_kb(kb);
-      }
+    for (int kb = kb_issued; kb < KB; ++kb) {
+      mbar_wait(empty_bar(ps), pph);
+      issue_kb(kb);
     }
   } else {
     // =============================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % S;
-        mbar_wait(full_bar(s), (uint32_t)((kb / S) & 1));
-        tc_fence_after();
-        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-        const uint32_t b_addr = a_addr + b_off;
-        for (int q = 0; q < nvalid; ++q) {
-          const uint32_t aq = a_addr + (uint32_t)q * TC_A_BYTES;
+    const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN);
+    // K-major SWIZZLE_128B descriptors as (high, low) words: high = SBO 1024 >> 4 | version 1 << 14 | layout 2 << 29,
+    // low = addr >> 4 | LBO 1 << 16; the four K slices of a k-block are +32 B = +2 units
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t lo0 = (smem_base >> 4) | (1u << 16);
+    const uint32_t stage_units = stage_bytes >> 4, b_units = b_off >> 4, aq_units = (uint32_t)TC_A_BYTES >> 4;
+    int s = 0;
+    uint32_t ph = 0, lo = lo0;
+    for (int kb = 0; kb < KB; ++kb) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (leader) {
+        if (!p.im2col) {
+          uint32_t alo = lo, dcol = tmem_acc;
+          for (int q = 0; q < nvalid; ++q, alo += aq_units, dcol += (uint32_t)p.BN) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_tf32(tmem_acc + (uint32_t)(q * p.BN), p.im2col ? make_sw32_kmajor_desc(aq + kk * 4096) : make_sw128_kmajor_desc(aq + kk * 32),
-                      make_sw128_kmajor_desc(b_addr + kk * 32), idesc, (uint32_t)((kb | kk) != 0));
+            for (int kk = 0; kk < 4; ++kk)
+              umma_tf32(dcol, ((uint64_t)hi << 32) | (alo + 2u * kk), ((uint64_t)hi << 32) | (lo + b_units + 2u * kk), idesc,
+                        (uint32_t)((kb | kk) != 0));
+          }
+        } else {
+          const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+          for (int q = 0; q < nvalid; ++q) {
+            const uint32_t aq = a_addr + (uint32_t)q * TC_A_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_tf32(tmem_acc + (uint32_t)(q * p.BN), make_sw32_kmajor_desc(aq + kk * 4096), make_sw128_kmajor_desc(a_addr + b_off + kk * 32),
+                        idesc, (uint32_t)((kb | kk) != 0));
+          }
         }
         umma_commit(empty_bar(s));
       }
-      umma_commit(tmem_full_bar);
+      lo += stage_units;
+      if (++s == S) { s = 0; ph ^= 1u; lo = lo0; }
     }
+    if (leader) umma_commit(tmem_full_bar);
   }
   tc_fence_before();
   __syncthreads();
@@ -1710,7 +1735,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3)
 conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constant__ WTmaMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int S = p.stages;
   const int ncg = p.Nc >> 5;
   // patch == 2 (stride 2, k = 4, TT = 4 or 8): np parity planes (tap-row ai, column parity pb), each 4 x 9 pixels, serve the
@@ -1793,73 +1818,102 @@ conv_wgrad_tma_kernel(const __grid_constant__ WTmaParams p, const __grid_constan
     }
   } else if (warp == 4) {
     // =============================================================== TMA producer: G tile + TT gathered X tiles per stage
-    if (lane == 0) {
-      const int per_img = p.tiles_x * p.tiles_y;
-      const uint32_t tx_bytes = WTC_A_BYTES + (p.patch ? (uint32_t)(np * ncg) * (uint32_t)(p.pw * p.ph) * 128u : b_bytes);
-      for (int st = 0; st < steps; ++st) {
-        const int s = st % S;
-        mbar_wait(empty_bar(s), (uint32_t)(((st / S) & 1) ^ 1));
+    // (warp-uniform loop, elected issuer, (slot, parity) ring counters and an incrementally tracked tile position: a lone
+    // warp issues about one dependent instruction per 4-6 clocks, so divisions in these loops are what the stage rate is)
+    const bool leader = elect_one_lane();
+    const int per_img = p.tiles_x * p.tiles_y;
+    const uint32_t tx_bytes = WTC_A_BYTES + (p.patch ? (uint32_t)(np * ncg) * (uint32_t)(p.pw * p.ph) * 128u : b_bytes);
+    int n = (int)(tbeg / per_img);
+    int r2 = (int)(tbeg - (long long)n * per_img);
+    int tyi = r2 / p.tiles_x, txi = r2 - tyi * p.tiles_x;
+    const int a0p = p.patch == 2 ? t0 / 4 : (p.patch ? t0 / p.k : 0);
+    const int b0p = (p.patch == 1 && p.TT <= p.k) ? t0 - a0p * p.k : 0;
+    int s = 0;
+    uint32_t ph = 1;
+    for (int st = 0; st < steps; ++st) {
+      mbar_wait(empty_bar(s), ph);
+      if (leader) {
         mbar_arrive_expect_tx(full_bar(s), tx_bytes);
-        const long long t = tbeg + st;
-        const int n = (int)(t / per_img);
-        const int r2 = (int)(t - (long long)n * per_img);
-        const int ty0 = (r2 / p.tiles_x) * WT_H, tx0 = (r2 % p.tiles_x) * WT_W;
+        const int ty0 = tyi * WT_H, tx0 = txi * WT_W;
         const uint32_t abase = smem_base + (uint32_t)s * stage_bytes;
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) tma_load_4d(abase + g4 * WTC_BLK, &maps.g, mch0 + g4 * 32, tx0, ty0, n, full_bar(s));
         const uint32_t bbase = abase + WTC_A_BYTES;
         if (p.patch == 2) {
-          const int a0 = t0 / 4;
           for (int pl = 0; pl < np; ++pl) {
             const int ai = pl >> 1, pb = pl & 1;
             for (int cg = 0; cg < ncg; ++cg)
               tma_load_4d(bbase + (uint32_t)(pl * ncg + cg) * p.blk_stride, &maps.x, c0 + cg * 32, tx0 * 2 + pb + p.off,
-                          ty0 * 2 + a0 + ai + p.off, n, full_bar(s));
+                          ty0 * 2 + a0p + ai + p.off, n, full_bar(s));
           }
         } else if (p.patch) {
-          const int a0 = t0 / p.k, b0 = (p.TT <= p.k) ? t0 - a0 * p.k : 0;
           for (int cg = 0; cg < ncg; ++cg)
-            tma_load_4d(bbase + (uint32_t)cg * p.blk_stride, &maps.x, c0 + cg * 32, tx0 + b0 + p.off, ty0 + a0 + p.off, n, full_bar(s));
+            tma_load_4d(bbase + (uint32_t)cg * p.blk_stride, &maps.x, c0 + cg * 32, tx0 + b0p + p.off, ty0 + a0p + p.off, n, full_bar(s));
         } else {
+          int a = t0 / p.k, b = t0 - a * p.k;
+          uint32_t dst = bbase;
           for (int ti = 0; ti < p.TT; ++ti) {
-            const int tap = t0 + ti;
-            const int a = tap / p.k, b = tap - a * p.k;
-            for (int cg = 0; cg < ncg; ++cg)
-              tma_load_4d(bbase + (uint32_t)(ti * ncg + cg) * WTC_BLK, &maps.x, c0 + cg * 32, tx0 * p.s + b + p.off,
-                          ty0 * p.s + a + p.off, n, full_bar(s));
+            for (int cg = 0; cg < ncg; ++cg, dst += WTC_BLK)
+              tma_load_4d(dst, &maps.x, c0 + cg * 32, tx0 * p.s + b + p.off, ty0 * p.s + a + p.off, n, full_bar(s));
+            if (++b == p.k) { b = 0; ++a; }
           }
         }
       }
+      if (++txi == p.tiles_x) { txi = 0; if (++tyi == p.tiles_y) { tyi = 0; ++n; } }
+      if (++s == S) { s = 0; ph ^= 1u; }
     }
   } else {
     // =============================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_mn(128, p.Nc);
-      for (int st = 0; st < steps; ++st) {
-        const int s = st % S;
-        mbar_wait(full_bar(s), (uint32_t)((st / S) & 1));
-        tc_fence_after();
-        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-        const uint32_t b_addr = a_addr + WTC_A_BYTES;
-        for (int ti = 0; ti < p.TT; ++ti) {
-          const int ai = p.patch ? ti / p.nb : 0, bi = p.patch ? ti - ai * p.nb : 0;
+    const bool leader = elect_one_lane();
+    const uint32_t idesc = make_idesc_tf32_mn(128, p.Nc);
+    // SWIZZLE_128B_BASE32B MN-major descriptors as (high word, low word): low = addr >> 4 | (LBO >> 4) << 16,
+    // high = SBO >> 4 | version 1 << 14 | layout 1 << 29
+    const uint32_t hi = (512u >> 4) | (1u << 14) | (1u << 29);
+    const uint32_t a_lbo = ((uint32_t)WTC_BLK >> 4) << 16;
+    const uint32_t b_lbo = ((p.patch ? p.blk_stride : (uint32_t)WTC_BLK) >> 4) << 16;
+    const uint32_t stage_units = stage_bytes >> 4;
+    const uint32_t a_lo0 = (smem_base >> 4) | a_lbo, b_lo0 = ((smem_base + WTC_A_BYTES) >> 4) | b_lbo;
+    const uint32_t kg_units = p.patch ? (uint32_t)p.pw * 8u : 64u;        // k-group = next patch row / next 1024-B block
+    int s = 0;
+    uint32_t ph = 0, a_lo = a_lo0, b_lo = b_lo0;
+    for (int st = 0; st < steps; ++st) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (leader) {
+        if (p.patch == 2) {
+          for (int ti = 0; ti < p.TT; ++ti) {
+            const int ai = ti / p.nb, bi = ti - ai * p.nb;
 #pragma unroll
-          for (int kg = 0; kg < 4; ++kg) {
-            uint64_t bdesc;
-            if (p.patch == 2)   // plane (ai, bi & 1), shifted by bi >> 1 pixels; k-group kg = plane row kg
-              bdesc = make_sw128b32_mnmajor_desc(b_addr + (uint32_t)((ai * 2 + (bi & 1)) * ncg) * p.blk_stride +
-                                                     (uint32_t)((kg * p.pw + (bi >> 1)) * 128), p.blk_stride, 512u);
-            else
-              bdesc = p.patch ? make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(((kg + ai) * p.pw + bi) * 128), p.blk_stride, 512u)
-                              : make_sw128b32_mnmajor_desc(b_addr + (uint32_t)(ti * ncg) * WTC_BLK + kg * 1024, WTC_BLK, 512u);
-            umma_tf32(tmem_acc + (uint32_t)(ti * p.Nc), make_sw128b32_mnmajor_desc(a_addr + kg * 1024, WTC_BLK, 512u), bdesc, idesc,
-                      (uint32_t)((st | kg) != 0));
+            for (int kg = 0; kg < 4; ++kg) {
+              // plane (ai, bi & 1), shifted by bi >> 1 pixels; k-group kg = plane row kg
+              const uint32_t bl = b_lo + (((uint32_t)((ai * 2 + (bi & 1)) * ncg) * p.blk_stride + (uint32_t)((kg * p.pw + (bi >> 1)) * 128)) >> 4);
+              umma_tf32(tmem_acc + (uint32_t)(ti * p.Nc), ((uint64_t)hi << 32) | (a_lo + 64u * kg), ((uint64_t)hi << 32) | bl, idesc,
+                        (uint32_t)((st | kg) != 0));
+            }
+          }
+        } else {
+          // tap ti: patch mode -> shifted start (ai * pw + bi) rows of 128 B; tile mode -> its own ncg blocks
+          uint32_t bt = b_lo, dcol = tmem_acc;
+          int bi = 0;
+          for (int ti = 0; ti < p.TT; ++ti, dcol += (uint32_t)p.Nc) {
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg)
+              umma_tf32(dcol, ((uint64_t)hi << 32) | (a_lo + 64u * kg), ((uint64_t)hi << 32) | (bt + kg_units * kg), idesc,
+                        (uint32_t)((st | kg) != 0));
+            if (p.patch) {
+              bt += 8u;                                                      // next tap column: one pixel row further
+              if (++bi == p.nb) { bi = 0; bt += (uint32_t)(p.pw - p.nb) * 8u; }  // next tap row
+            } else {
+              bt += (uint32_t)ncg * ((uint32_t)WTC_BLK >> 4);
+            }
           }
         }
         umma_commit(empty_bar(s));
       }
-      if (steps > 0) umma_commit(tmem_full_bar);
+      a_lo += stage_units; b_lo += stage_units;
+      if (++s == S) { s = 0; ph ^= 1u; a_lo = a_lo0; b_lo = b_lo0; }
     }
+    if (steps > 0 && leader) umma_commit(tmem_full_bar);
   }
   tc_fence_before();
   __syncthreads();
