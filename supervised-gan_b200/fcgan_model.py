@@ -247,8 +247,8 @@ class FCGANModel(object):
         self.optimizer_G.sync_hyper()
         g_fwd.replay()
         self._wait_input()
-        # This step's pool decisions (Python `random`, the reference's order).  AFTER the first graph: the plan buffers were
-        # allocated while capturing g_upd from the pool both graphs share, where they may alias temporaries of g_fwd.
+        # this step's pool decisions (Python `random`, the reference's order) into the plan buffers the captured pool kernel
+        # reads (ordinary allocations made by the eager warm-up queries, not graph-pool memory: image_pool.py)
         self.fake_pool.prepare_replay()
         g_upd.replay()
         ops.bump_weights_epoch()

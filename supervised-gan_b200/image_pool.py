@@ -24,6 +24,7 @@ class ImagePool():
         self._plan_dev = None       # int32 [B]: -1 pass through, 2*slot store, 2*slot+1 swap (eager queries)
         self._plan_host = None
         self._graph_plans = []      # [dev int32 [B], last host plan] of every query captured into a CUDA graph, in order
+        self._reserve = []          # plan buffers allocated by EAGER queries for later captures (see query())
 
     # ------------------------------------------------------------------ host side: decisions
     def _draw(self, batch):
@@ -53,9 +54,6 @@ class ImagePool():
         """Before replaying a CUDA graph that contains this pool's queries: draws the decisions of every captured query,
         in capture order, and writes them into the plan buffers the captured kernels read."""
         for slot in self._graph_plans:
-            # always rewritten: a buffer allocated while capturing lives in the graph's memory pool, where another graph
-            # sharing that pool (the step drivers capture the generator forward separately) may use the same bytes as a
-            # temporary -- call this AFTER such graphs have replayed and right before the one holding the query
             self._upload(slot, self._draw(slot[0].numel()), force=True)
 
     # ------------------------------------------------------------------ device side
@@ -78,11 +76,21 @@ class ImagePool():
             self.images = torch.zeros((self.pool_size,) + tuple(src.shape[1:]), dtype=torch.float32, device=src.device)
             self.num_imgs = 0
         if capturing:
-            # one plan buffer per captured query (its address is baked into the graph); filled by prepare_replay()
-            slot = [torch.empty(B, dtype=torch.int32, device=src.device), None]   # empty: a fill would be captured too
+            # One plan buffer per captured query (its address is baked into the graph); filled by prepare_replay() BEFORE
+            # the replay.  It must not come from the graph's own memory pool: a block allocated while capturing may reuse
+            # the bytes of a temporary that an EARLIER kernel of the same graph writes, which would clobber the uploaded
+            # plan before the pool kernel reads it (out-of-range slots -> illegal address).  The eager warm-up queries
+            # therefore set aside ordinary allocations for the capture to use.
+            while self._reserve and (self._reserve[-1].numel() != B or self._reserve[-1].device != src.device):
+                self._reserve.pop()
+            if not self._reserve:
+                raise RuntimeError("ImagePool: run at least one eager step with this batch size before graph capture")
+            slot = [self._reserve.pop(), None]
             self._graph_plans.append(slot)
             plan_dev = slot[0]
         else:
+            if len(self._reserve) < 8:
+                self._reserve.append(torch.empty(B, dtype=torch.int32, device=src.device))
             if self._plan_dev is None or self._plan_dev.numel() != B or self._plan_dev.device != src.device:
                 self._plan_dev, self._plan_host = torch.empty(B, dtype=torch.int32, device=src.device), None
             slot = [self._plan_dev, self._plan_host]
