@@ -219,6 +219,19 @@ int sgk_bce_pair_loss(const float* x, const float* t, size_t n, float* loss_out,
 int sgk_image_pool_query(const float* images, float* pool, const int32_t* plan_dev, float* out, int B,
                          long long per_image, int pool_size, void* stream);
 
+/* ---------------------------------------------------------------- input pipeline and loss weights
+ * data/base_dataset.py:17-55 get_transform + the channel selection of set_input (fcgan_model.py:118-122; cgan_model.py:66-72):
+ * one decoded uint8 HWC image (device or pinned host memory) -> fp32 [nsel][S][S] planes of an NCHW batch:
+ * crop S x S at (y0, x0) -> horizontal flip -> rotation by 90*rot degrees counter-clockwise (PIL's exact transposes) ->
+ * ToTensor (v / 255) -> Normalize ((t - 0.5) / 0.5), bit-identical to the reference's fp32 arithmetic.
+ * chan_host: HOST array of the nsel (1..4) source channels to keep, in output order. */
+int sgk_image_transform_u8(const uint8_t* src, int H0, int W0, int C0, float* dst, int S, int y0, int x0, int flip,
+                           int rot, const int* chan_host, int nsel, void* stream);
+/* weight = 1 + sum_i ((real_A_i + 1) / 2) (weights_i - 1) (cgan_model.py:197-206; twostage_cycle_model.py:362-370):
+ * real_a [N][C][HW] (NCHW), weight [N][1][HW]; weights_host: HOST array of nw (<= min(4, C)) class weights. */
+int sgk_l1_weight_map(const float* real_a, float* weight, int N, int C, long long HW, const float* weights_host, int nw,
+                      void* stream);
+
 /* ---------------------------------------------------------------- optimiser
  * torch.optim.Adam (fcgan_model.py:98-109; cgan_model.py:95-108; twostage_cycle_model.py:149-166):
  * multi-tensor launches (metadata passed by value as kernel parameters, so a captured CUDA graph carries it).

@@ -337,3 +337,28 @@ def adam_step(p, g, m, v, step, lr, beta1=0.5, beta2=0.999, eps=1e-8):
     denom = np.sqrt(v) / np.sqrt(bc2) + eps
     p = p - (lr / bc1) * m / denom
     return p, m, v
+
+
+# ----------------------------------------------------------------------------
+# input pipeline: data/base_dataset.py:17-43 get_transform (RandomCrop -> RandomHorizontalFlip -> rotate(90 k) -> ToTensor ->
+# Normalize(0.5, 0.5)) followed by the channel selection of set_input (fcgan_model.py:118-122)
+# ----------------------------------------------------------------------------
+def image_transform(img_u8, S, y0, x0, flip, rot, chans):
+    """img_u8: uint8 [H, W, C].  Returns float32 [len(chans), S, S] -- fp32 on purpose: ToTensor / Normalize are fp32 ops and
+    the kernel must match them bit for bit."""
+    a = np.asarray(img_u8)[y0:y0 + S, x0:x0 + S, :]
+    if flip:
+        a = a[:, ::-1, :]
+    a = np.rot90(a, k=rot % 4, axes=(0, 1))            # counter-clockwise, like PIL.Image.rotate
+    t = a.astype(np.float32) / np.float32(255.0)       # ToTensor
+    t = (t - np.float32(0.5)) / np.float32(0.5)        # Normalize
+    return np.ascontiguousarray(np.transpose(t, (2, 0, 1))[list(chans)])
+
+
+def l1_weight_map(real_a, weights):
+    """1 + sum_i ((a_i + 1) / 2) (w_i - 1)  (cgan_model.py:197-206); real_a [N, C, H, W] -> [N, 1, H, W]."""
+    a = (np.asarray(real_a, dtype=np.float64) + 1) / 2
+    w = np.ones((a.shape[0], 1) + a.shape[2:])
+    for i, wi in enumerate(weights):
+        w = w + a[:, i:i + 1] * (wi - 1.0)
+    return w

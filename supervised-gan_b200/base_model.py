@@ -1,10 +1,11 @@
 """Shared plumbing of the step drivers (reference: models/base_model.py:8-64): device handling, the
 `which_channel` parser, reference-compatible '<epoch>_net_<label>.pth' checkpoints, linear lr decay."""
+import ctypes
 import os
 
 import torch
 
-from . import networks, ops
+from . import _lib, networks, ops
 
 
 def save_optimizer(optimizer, save_dir, label, epoch_label):
@@ -64,13 +65,18 @@ class BaseModel(object):
         return (lambda x: x), (lambda x: x)
 
     def l1_weight_map(self, real_A):
-        """weight = 1 + sum_i ((real_A_i + 1) / 2) (weights_i - 1)  (cgan_model.py:197-206)."""
+        """weight = 1 + sum_i ((real_A_i + 1) / 2) (weights_i - 1)  (cgan_model.py:197-206), one kernel."""
         if self.opt.weights is None:
             return None
-        a = (real_A.detach() + 1) / 2
-        weight = torch.ones(a.shape[0], 1, a.shape[2], a.shape[3], device=a.device)
-        for i in range(len(self.opt.weights)):
-            weight = weight + a.narrow(1, i, 1) * (self.opt.weights[i] - 1.0)
+        a = real_A.detach()
+        a = a if a.is_contiguous() else a.contiguous()
+        ws = [float(w) for w in self.opt.weights]
+        if a.dtype != torch.float32 or not a.is_cuda or not 1 <= len(ws) <= min(4, a.shape[1]):
+            raise RuntimeError("l1_weight_map: fp32 CUDA real_A with 1..min(4, C) class weights expected")
+        weight = torch.empty(a.shape[0], 1, a.shape[2], a.shape[3], device=a.device)
+        arr = (ctypes.c_float * len(ws))(*ws)
+        _lib.check(_lib.load().sgk_l1_weight_map(a.data_ptr(), weight.data_ptr(), a.shape[0], a.shape[1], a.shape[2] * a.shape[3],
+                                                 arr, len(ws), torch.cuda.current_stream().cuda_stream), "l1_weight_map")
         return weight
 
     def _draw(self, buf, shape):

@@ -199,8 +199,9 @@ class FCGANModel(object):
             B = real.shape[0]
             both = self._both_batch(real)
             self.fake_pool.query(self.fake, out=both[:B])     # the pool kernel writes the fake half in place
+            both_cl = ops.to_nhwc(both)                       # one channels-last copy for all scales
             for netD in self.netD:
-                pred = netD.forward(both)
+                pred = netD.forward_nhwc(both_cl)
                 self.loss_D_fake = self.loss_D_fake + self.criterionGAN(pred[:B], False)
                 self.loss_D_real = self.loss_D_real + self.criterionGAN(pred[B:], True)
         else:
@@ -219,8 +220,9 @@ class FCGANModel(object):
             for p in self.params_D:
                 p.requires_grad_(False)
         try:
+            fake_cl = ops.to_nhwc(fake)
             for netD, lambda_D in zip(self.netD, self.opt.lambda_D):
-                pred_fake = netD.forward(fake)
+                pred_fake = netD.forward_nhwc(fake_cl)
                 if not self.opt.no_logD_trick:
                     self.loss_G = self.loss_G + self.criterionGAN(pred_fake, True) * lambda_D
                 else:

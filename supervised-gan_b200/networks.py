@@ -480,6 +480,11 @@ class NLayerDiscriminator(nn.Module):
     def forward(self, x):
         return ops.to_nchw(self._fwd(ops.to_nhwc(x)))
 
+    def forward_nhwc(self, x_nhwc):
+        """Same as forward() for an input that is already channels-last ([N, H, W, C], from ops.to_nhwc): the step drivers
+        convert a batch once and show it to every scale of the multi-scale discriminator."""
+        return ops.to_nchw(self._fwd(x_nhwc))
+
 
 class UnetGenerator(nn.Module):
     # networks.py:318-367

@@ -404,3 +404,58 @@ def test_pack_weight_multi_matches_single(S):
     torch.cuda.synchronize()
     for (d, op, w, b), a in zip(jobs, singles):
         assert torch.equal(a, b)
+
+
+def test_image_transform_kernel_is_bit_exact(S, tmp_path):
+    """sgk_image_transform_u8 (GPU input pipeline) against the oracle for every flip / rotation, a channel subset, and the
+    dataset wrapper's draw order against a host re-implementation of get_transform's list (data/base_dataset.py:17-43)."""
+    import argparse
+    import random
+    from supervised_gan_b200 import data as D
+    rng = np.random.RandomState(7)
+    img = rng.randint(0, 256, size=(70, 96, 3)).astype(np.uint8)
+    dimg = torch.from_numpy(img).cuda()
+    opt = argparse.Namespace(fineSize=48, loadSize=64, resize_or_crop="crop", isTrain=True, no_flip=False, no_rotate=False)
+    for chans in [(0, 1, 2), (0, 1), (2,)]:
+        tr = D.GpuTransform(opt, chans)
+        for flip in (0, 1):
+            for rot in range(4):
+                got = tr(dimg, params=(9, 13, flip, rot)).cpu().numpy()
+                assert np.array_equal(got, O.image_transform(img, 48, 9, 13, flip, rot, chans)), (chans, flip, rot)
+    # random decisions: same `random` stream as the reference's transform list (crop top, crop left, flip, rotation)
+    random.seed(123)
+    got = D.GpuTransform(opt)(dimg).cpu().numpy()
+    random.seed(123)
+    y0 = random.randint(0, 70 - 48); x0 = random.randint(0, 96 - 48); flip = random.random() < 0.5; rot = random.randint(0, 3)
+    assert np.array_equal(got, O.image_transform(img, 48, y0, x0, int(flip), rot, (0, 1, 2)))
+    # dataset wrapper: PNG files -> decoded once -> batch written in place
+    from PIL import Image
+    os_dir = tmp_path / "train"
+    os_dir.mkdir()
+    imgs = [rng.randint(0, 256, size=(64, 64, 3)).astype(np.uint8) for _ in range(3)]
+    for i, a in enumerate(imgs):
+        Image.fromarray(a).save(str(os_dir / ("%02d.png" % i)))
+    opt2 = argparse.Namespace(fineSize=48, loadSize=64, resize_or_crop="crop", isTrain=True, no_flip=False, no_rotate=True,
+                              dataroot=str(tmp_path), phase="train")
+    ds = D.GpuSingleDataset().initialize(opt2)
+    assert len(ds) == 3
+    random.seed(5)
+    b = ds.batch([2, 0])
+    random.seed(5)
+    for k, i in enumerate([2, 0]):
+        y0 = random.randint(0, 16); x0 = random.randint(0, 16); flip = random.random() < 0.5
+        assert np.array_equal(b["A"][k].cpu().numpy(), O.image_transform(imgs[i], 48, y0, x0, int(flip), 0, (0, 1, 2)))
+    with pytest.raises(RuntimeError):
+        D.GpuTransform(opt)(torch.from_numpy(img))          # host image: no CPU fallback
+
+
+def test_l1_weight_map_kernel(S):
+    rng = np.random.RandomState(8)
+    a = rng.uniform(-1, 1, size=(2, 3, 33, 17))
+    import ctypes
+    from supervised_gan_b200 import _lib as L
+    ta = dev(a)
+    w = torch.empty(2, 1, 33, 17, device="cuda")
+    arr = (ctypes.c_float * 2)(2.0, 4.0)
+    L.check(L.load().sgk_l1_weight_map(ta.data_ptr(), w.data_ptr(), 2, 3, 33 * 17, arr, 2, torch.cuda.current_stream().cuda_stream), "wm")
+    close(w.cpu().numpy(), O.l1_weight_map(a, [2.0, 4.0]), 2e-6, "l1 weight map")

@@ -158,3 +158,33 @@ def test_adam():
         opt.step()
         p, m, v = O.adam_step(p, g, m, v, step, 2e-4)
         close(p, pt, 1e-12)
+
+
+@pytest.mark.parametrize("flip,rot", [(0, 0), (1, 0), (0, 1), (1, 2), (0, 3), (1, 3)])
+def test_image_transform_matches_pil_pipeline(flip, rot):
+    """The oracle's crop / flip / rotate / ToTensor / Normalize against the PIL calls torchvision's transforms make
+    (data/base_dataset.py:17-55): Image.crop, transpose(FLIP_LEFT_RIGHT), rotate(90 k, BILINEAR, expand=0), then the fp32
+    arithmetic of ToTensor (div 255) and Normalize ((t - 0.5) / 0.5)."""
+    from PIL import Image
+    rng = np.random.RandomState(5)
+    img = rng.randint(0, 256, size=(40, 52, 3)).astype(np.uint8)
+    S, y0, x0 = 24, 7, 11
+    pil = Image.fromarray(img).crop((x0, y0, x0 + S, y0 + S))
+    if flip:
+        pil = pil.transpose(Image.FLIP_LEFT_RIGHT)
+    pil = pil.rotate(90 * rot, resample=Image.BILINEAR, expand=0)
+    t = torch.from_numpy(np.asarray(pil, dtype=np.uint8).copy()).permute(2, 0, 1).float().div(255)
+    t = (t - 0.5) / 0.5
+    got = O.image_transform(img, S, y0, x0, flip, rot, (0, 1, 2))
+    assert got.dtype == np.float32 and np.array_equal(got, t.numpy())
+    assert np.array_equal(O.image_transform(img, S, y0, x0, flip, rot, (2, 0)), t.numpy()[[2, 0]])
+
+
+def test_l1_weight_map_oracle_matches_torch():
+    rng = np.random.RandomState(6)
+    a = rng.uniform(-1, 1, size=(2, 3, 5, 7))
+    ta = torch.from_numpy(a)
+    w = torch.ones(2, 1, 5, 7, dtype=torch.float64)
+    for i, wi in enumerate([2.0, 4.0]):
+        w = w + ((ta + 1) / 2).narrow(1, i, 1) * (wi - 1.0)
+    np.testing.assert_allclose(O.l1_weight_map(a, [2.0, 4.0]), w.numpy(), rtol=0, atol=1e-15)
