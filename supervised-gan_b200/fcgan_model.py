@@ -96,6 +96,12 @@ class FCGANModel(object):
                 load_optimizer(self.optimizer_D, self.save_dir, 'D', opt.which_epoch, self.device)
         self.batch_D_passes = getattr(opt, "batch_D_passes", True) and opt.norm == 'instance'
         self.skip_unused_grads = getattr(opt, "skip_unused_grads", True)
+        # the discriminator scales are independent given the batch: run them on parallel streams (forked from / joined to the
+        # current one, so a CUDA-graph capture records parallel branches) -- the launch-bound 128^2 / 256^2 scales then hide
+        # inside the 512^2 scale's long kernels.  Autograd runs each backward node on its forward stream.
+        self.parallel_D = (bool(getattr(opt, "parallel_D", True)) and os.environ.get("SGK_PARALLEL_D", "1") != "0"
+                           and self.isTrain and len(getattr(self, "netD", [])) > 1)
+        self._d_streams = None
         self.grad_sync = None  # data-parallel hook: callable(list_of_params, tag) run between backward and step
         # opt.cuda_graph: after `graph_warmup` eager steps the whole step (G fwd, D phase, Adam, G phase, Adam -- and the
         # NCCL all-reduces under data parallelism) is captured once and replayed; nothing in the step touches the host.
@@ -200,10 +206,13 @@ class FCGANModel(object):
             both = self._both_batch(real)
             self.fake_pool.query(self.fake, out=both[:B])     # the pool kernel writes the fake half in place
             both_cl = ops.to_nhwc(both)                       # one channels-last copy for all scales
-            for netD in self.netD:
+
+            def one(netD):
                 pred = netD.forward_nhwc(both_cl)
-                self.loss_D_fake = self.loss_D_fake + self.criterionGAN(pred[:B], False)
-                self.loss_D_real = self.loss_D_real + self.criterionGAN(pred[B:], True)
+                return self.criterionGAN(pred[:B], False), self.criterionGAN(pred[B:], True)
+            for lf, lr_ in self._for_each_D(one):
+                self.loss_D_fake = self.loss_D_fake + lf
+                self.loss_D_real = self.loss_D_real + lr_
         else:
             fake = self.fake_pool.query(self.fake)
             for netD in self.netD:
@@ -221,17 +230,32 @@ class FCGANModel(object):
                 p.requires_grad_(False)
         try:
             fake_cl = ops.to_nhwc(fake)
-            for netD, lambda_D in zip(self.netD, self.opt.lambda_D):
-                pred_fake = netD.forward_nhwc(fake_cl)
-                if not self.opt.no_logD_trick:
-                    self.loss_G = self.loss_G + self.criterionGAN(pred_fake, True) * lambda_D
-                else:
-                    self.loss_G = self.loss_G + -self.criterionGAN(pred_fake, False) * lambda_D
+            trick = not self.opt.no_logD_trick
+            losses = self._for_each_D(lambda netD: self.criterionGAN(netD.forward_nhwc(fake_cl), trick))
+            for l, lambda_D in zip(losses, self.opt.lambda_D):
+                self.loss_G = self.loss_G + (l if trick else -l) * lambda_D
             self.loss_G.backward()
         finally:
             if self.skip_unused_grads:
                 for p in self.params_D:
                     p.requires_grad_(True)
+
+    def _for_each_D(self, fn):
+        """[fn(netD) for netD in self.netD]; with parallel_D every scale but the first runs on its own stream."""
+        if not self.parallel_D:
+            return [fn(netD) for netD in self.netD]
+        main = torch.cuda.current_stream()
+        if self._d_streams is None:
+            self._d_streams = [torch.cuda.Stream() for _ in self.netD[1:]]
+        outs = [None] * len(self.netD)
+        for i, s in enumerate(self._d_streams, start=1):      # small scales first: they are the launch-bound ones
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                outs[i] = fn(self.netD[i])
+        outs[0] = fn(self.netD[0])
+        for s in self._d_streams:
+            main.wait_stream(s)
+        return outs
 
     def _wait_input(self):
         """The batch of set_input may still be in flight on the copy stream: order the current stream after it."""
