@@ -100,6 +100,32 @@ class BaseModel(object):
                 for p in self.params:
                     p.requires_grad_(True)
 
+    # ------------------------------------------------------------------ parallel discriminator scales
+    def _for_each_net(self, nets, fn):
+        """[fn(net) for net in nets] with every net but the first on its own CUDA stream, forked from and joined to the current
+        stream (parallel branches of a captured graph).  The scales of a multi-scale discriminator are independent given their
+        input, and the small ones are launch-bound: they hide inside the full-resolution scale's kernels.  Autograd runs each
+        backward node on the stream of its forward, so the backward passes overlap the same way.  opt.parallel_D / SGK_PARALLEL_D=0
+        turn it off."""
+        if getattr(self, "_parallel_D", None) is None:
+            self._parallel_D = bool(getattr(self.opt, "parallel_D", True)) and os.environ.get("SGK_PARALLEL_D", "1") != "0"
+            self._net_streams = []
+        if not self._parallel_D or len(nets) < 2 or not torch.cuda.is_available():
+            return [fn(net) for net in nets]
+        while len(self._net_streams) < len(nets) - 1:
+            self._net_streams.append(torch.cuda.Stream())
+        main = torch.cuda.current_stream()
+        outs = [None] * len(nets)
+        for i in range(1, len(nets)):
+            st = self._net_streams[i - 1]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                outs[i] = fn(nets[i])
+        outs[0] = fn(nets[0])
+        for i in range(1, len(nets)):
+            main.wait_stream(self._net_streams[i - 1])
+        return outs
+
     # ------------------------------------------------------------------ step execution (eager / CUDA graph)
     def optimize_parameters(self):
         """The reference's optimize_parameters (cgan_model.py:210-225, twostage_cycle_model.py:412-438) is the subclass's

@@ -104,13 +104,14 @@ class CGANModel(BaseModel):
 
     def backward_D(self):
         fake = self.fake_pool.query(self._pair(self.real_A, self.fake_B))
-        self.loss_D_fake = 0
-        for netD in self.netD:
-            self.loss_D_fake = self.loss_D_fake + self.criterionGAN(netD.forward(fake.detach()), False)
         real = self._pair(self.real_A, self.real_B)
+        fake_d = fake.detach()
+        self.loss_D_fake = 0
         self.loss_D_real = 0
-        for netD in self.netD:
-            self.loss_D_real = self.loss_D_real + self.criterionGAN(netD.forward(real), True)
+        for lf, lr_ in self._for_each_net(self.netD, lambda netD: (self.criterionGAN(netD.forward(fake_d), False),
+                                                                   self.criterionGAN(netD.forward(real), True))):
+            self.loss_D_fake = self.loss_D_fake + lf
+            self.loss_D_real = self.loss_D_real + lr_
         self.loss_D = (self.loss_D_fake + self.loss_D_real) * 0.5
         self.loss_D.backward()
 
@@ -118,12 +119,10 @@ class CGANModel(BaseModel):
         fake = self._pair(self.real_A, self.fake_B)
         self.loss_G = 0
         with self.frozen(self.params_D, self.skip_unused_grads):
-            for netD, lambda_D in zip(self.netD, self.opt.lambda_D):
-                pred_fake = netD.forward(fake)
-                if not self.opt.no_logD_trick:
-                    self.loss_G = self.loss_G + self.criterionGAN(pred_fake, True) * lambda_D
-                else:
-                    self.loss_G = self.loss_G + -self.criterionGAN(pred_fake, False) * lambda_D
+            trick = not self.opt.no_logD_trick
+            for l, lambda_D in zip(self._for_each_net(self.netD, lambda netD: self.criterionGAN(netD.forward(fake), trick)),
+                                   self.opt.lambda_D):
+                self.loss_G = self.loss_G + (l if trick else -l) * lambda_D
             weight = self.l1_weight_map(self.real_A)
             self.loss_G_L1 = self.criterionL1(self.fake_B, self.real_B, weight) * self.opt.lambda_A
             self.loss_G = self.loss_G + self.loss_G_L1

@@ -148,13 +148,14 @@ class TwoStageCycleModel(BaseModel):
 
     def backward_D1(self):
         fake = self.fake_pool1.query(self.fake_A)
-        self.loss_D1_fake = 0
-        for netD in self.netD1:
-            self.loss_D1_fake = self.loss_D1_fake + self.criterionGAN1(netD.forward(fake.detach()), False)
         real = self.transform_inverse(self.real_A)
+        fake_d = fake.detach()
+        self.loss_D1_fake = 0
         self.loss_D1_real = 0
-        for netD in self.netD1:
-            self.loss_D1_real = self.loss_D1_real + self.criterionGAN1(netD.forward(real), True)
+        for lf, lr_ in self._for_each_net(self.netD1, lambda netD: (self.criterionGAN1(netD.forward(fake_d), False),
+                                                                    self.criterionGAN1(netD.forward(real), True))):
+            self.loss_D1_fake = self.loss_D1_fake + lf
+            self.loss_D1_real = self.loss_D1_real + lr_
         self.loss_D1 = (self.loss_D1_fake + self.loss_D1_real) * 0.5
         self.loss_D1.backward()
 
@@ -164,18 +165,20 @@ class TwoStageCycleModel(BaseModel):
         if 'real_fake' in self.opt.GAN_losses_D2:
             fake = self.fake_pool2.query(self._pair(self.real_A, self.fake_B_from_real_A))
             num_fake_pairs += 1
-            for netD in self.netD2:
-                self.loss_D2_fake = self.loss_D2_fake + self.criterionGAN2(netD.forward(fake.detach()), False)
+            fake_d = fake.detach()
+            for l in self._for_each_net(self.netD2, lambda netD: self.criterionGAN2(netD.forward(fake_d), False)):
+                self.loss_D2_fake = self.loss_D2_fake + l
         if 'fake_fake' in self.opt.GAN_losses_D2:
             fake = self.fake_pool2.query(self._pair(self.transform(self.fake_A), self.fake_B_from_fake_A))
             num_fake_pairs += 1
-            for netD in self.netD2:
-                self.loss_D2_fake = self.loss_D2_fake + self.criterionGAN2(netD.forward(fake.detach()), False)
+            fake_d2 = fake.detach()
+            for l in self._for_each_net(self.netD2, lambda netD: self.criterionGAN2(netD.forward(fake_d2), False)):
+                self.loss_D2_fake = self.loss_D2_fake + l
         self.loss_D2_fake = self.loss_D2_fake / num_fake_pairs
         real = self._pair(self.real_A, self.real_B)
         self.loss_D2_real = 0
-        for netD in self.netD2:
-            self.loss_D2_real = self.loss_D2_real + self.criterionGAN2(netD.forward(real), True)
+        for l in self._for_each_net(self.netD2, lambda netD: self.criterionGAN2(netD.forward(real), True)):
+            self.loss_D2_real = self.loss_D2_real + l
         self.loss_D2 = (self.loss_D2_fake + self.loss_D2_real) * 0.5
         self.loss_D2.backward()
 
@@ -183,12 +186,10 @@ class TwoStageCycleModel(BaseModel):
         o = self.opt
         with self.frozen(self.params_D1 + self.params_D2, self.skip_unused_grads):
             self.loss_G1_GAN = 0
-            for netD, lambda_D in zip(self.netD1, o.lambda_D1):
-                pred_fake = netD.forward(self.fake_A)
-                if not o.no_logD_trick:
-                    self.loss_G1_GAN = self.loss_G1_GAN + self.criterionGAN1(pred_fake, True) * lambda_D
-                else:
-                    self.loss_G1_GAN = self.loss_G1_GAN + -self.criterionGAN1(pred_fake, False) * lambda_D
+            trick = not o.no_logD_trick
+            for l, lambda_D in zip(self._for_each_net(self.netD1, lambda netD: self.criterionGAN1(netD.forward(self.fake_A), trick)),
+                                   o.lambda_D1):
+                self.loss_G1_GAN = self.loss_G1_GAN + (l if trick else -l) * lambda_D
             self.loss_G2_GAN = 0
             num_fake_pairs = 0
             fakes = []
@@ -199,12 +200,9 @@ class TwoStageCycleModel(BaseModel):
                 fakes.append(self.fake_B_from_fake_A if o.no_cgan else torch.cat([self.transform(fa), self.fake_B_from_fake_A], 1))
             for fake in fakes:
                 num_fake_pairs += 1
-                for netD, lambda_D in zip(self.netD2, o.lambda_D2):
-                    pred_fake = netD.forward(fake)
-                    if not o.no_logD_trick:
-                        self.loss_G2_GAN = self.loss_G2_GAN + self.criterionGAN2(pred_fake, True) * lambda_D
-                    else:
-                        self.loss_G2_GAN = self.loss_G2_GAN + -self.criterionGAN2(pred_fake, False) * lambda_D
+                for l, lambda_D in zip(self._for_each_net(self.netD2, lambda netD, fake=fake: self.criterionGAN2(netD.forward(fake), trick)),
+                                       o.lambda_D2):
+                    self.loss_G2_GAN = self.loss_G2_GAN + (l if trick else -l) * lambda_D
             if 'real_fake' in o.GAN_losses_G2:
                 self.loss_G2_L1 = self.criterionL1(self.fake_B_from_real_A, self.real_B, self.l1_weight_map(self.real_A))
             else:
