@@ -232,6 +232,18 @@ int sgk_image_transform_u8(const uint8_t* src, int H0, int W0, int C0, float* ds
 int sgk_l1_weight_map(const float* real_a, float* weight, int N, int C, long long HW, const float* weights_host, int nw,
                       void* stream);
 
+/* ---------------------------------------------------------------- remaining architectures / inference
+ * nn.ReflectionPad2d(p) on NHWC (ResnetGenerator / ResnetBlock, networks.py:238,263,282,294); x [N][H][W][C] -> y [N][H+2p][W+2p][C];
+ * backward gathers the <= 2 x 2 mirrored positions per input pixel (deterministic). */
+int sgk_reflection_pad_fwd(const float* x, float* y, int N, int C, int H, int W, int p, void* stream);
+int sgk_reflection_pad_bwd(const float* dy, float* dx, int N, int C, int H, int W, int p, void* stream);
+/* util.tensor2im (util/util.py:15-25) of ONE image [C][H][W]: (x + 1) / 2 * 255 -> uint8 [H][W][3] (C = 1 repeated, C = 2 zero-padded). */
+int sgk_tensor2im_u8(const float* image_chw, uint8_t* out_hwc3, int C, int H, int W, void* stream);
+/* GANLossMultiClass (networks.py:188-202): CrossEntropyLoss of NCHW logits against ONE constant class per call;
+ * loss_out[0] = mean over N*HW pixels, grad = d(loss)/d(logits).  workspace: sgk_loss_workspace_bytes(). */
+int sgk_ce_const_loss(const float* logits, int N, int C, long long HW, int target, float* loss_out, float* grad,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- optimiser
  * torch.optim.Adam (fcgan_model.py:98-109; cgan_model.py:95-108; twostage_cycle_model.py:149-166):
  * multi-tensor launches (metadata passed by value as kernel parameters, so a captured CUDA graph carries it).

@@ -83,6 +83,10 @@ SIGNATURES = {
     "sgk_image_pool_query": (c_int, [P, P, P, P, c_int, ctypes.c_longlong, c_int, P]),
     "sgk_image_transform_u8": (c_int, [P, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P]),
     "sgk_l1_weight_map": (c_int, [P, P, c_int, c_int, ctypes.c_longlong, P, c_int, P]),
+    "sgk_reflection_pad_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "sgk_reflection_pad_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "sgk_tensor2im_u8": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "sgk_ce_const_loss": (c_int, [P, c_int, c_int, ctypes.c_longlong, c_int, P, P, P, c_size_t, P]),
     "sgk_adam_multi_tensor": (c_int, [POINTER(SgkAdamTensor), c_int, P, P, P]),
     "sgk_multi_tensor_pack": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, P, P]),
     "sgk_multi_tensor_unpack": (c_int, [P, POINTER(c_void_p), POINTER(c_int64), c_int, P]),

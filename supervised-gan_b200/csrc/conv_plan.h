@@ -67,8 +67,12 @@ inline int validate_desc(const SgkConvDesc& d) {
     ho = (d.Hin + 2 * d.pad - d.k) / d.stride + 1;
     wo = (d.Win + 2 * d.pad - d.k) / d.stride + 1;
   } else {
+    // ConvTranspose2d with output_padding op in [0, stride): Hout = (Hin - 1) s - 2 p + k + op.  Every such Hout is the input
+    // size of a direct conv (k, s, p) whose output is Hin, which is all the lowering needs (conv_plan.h: equivalent direct conv)
     ho = (d.Hin - 1) * d.stride - 2 * d.pad + d.k;
     wo = (d.Win - 1) * d.stride - 2 * d.pad + d.k;
+    if (d.Hout > ho && d.Hout < ho + d.stride) ho = d.Hout;
+    if (d.Wout > wo && d.Wout < wo + d.stride) wo = d.Wout;
   }
   if (ho != d.Hout || wo != d.Wout || ho <= 0 || wo <= 0) {
     set_error("SgkConvDesc: Hout/Wout (%d,%d) do not match k=%d s=%d p=%d on (%d,%d) -> (%d,%d)", d.Hout, d.Wout, d.k,

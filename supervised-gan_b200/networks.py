@@ -101,9 +101,16 @@ def define_G(input_nc, output_nc, ngf, which_model_netG, norm='batch', use_dropo
         # It ignores `norm` and hard-codes BatchNorm2d (networks.py:86-88).
         netG = FCGANGenerator(noise_nc, input_nc, ngf, n_layers=n_layers_G, norm_layer=BatchNorm2d,
                               use_dropout=use_dropout, use_fcn=use_fcn, gpu_ids=gpu_ids)
-    elif which_model_netG in ('resnet_9blocks', 'resnet_6blocks', 'autoencoder', 'fcgan_star', 'dcgan'):
-        raise NotImplementedError('Generator model name [%s] exists in the reference but is outside the B200 hot path '
-                                  '(fcgan/deconv, unet_128, unet_256, crn)' % which_model_netG)
+    elif which_model_netG in ('resnet_9blocks', 'resnet_6blocks'):
+        netG = ResnetGenerator(input_nc, output_nc, ngf, norm_layer=norm_layer, use_dropout=use_dropout,
+                               n_blocks=9 if which_model_netG == 'resnet_9blocks' else 6, use_residual=use_residual, gpu_ids=gpu_ids)
+    elif which_model_netG == 'autoencoder':
+        netG = AutoEncoder(input_nc, output_nc, n_layers_G, ngf, norm_layer=norm_layer, use_dropout=use_dropout, gpu_ids=gpu_ids)
+    elif which_model_netG == 'fcgan_star':
+        netG = FCGANGeneratorStar(noise_nc, input_nc, ngf, n_layers=n_layers_G, norm_layer=BatchNorm2d,
+                                  use_dropout=use_dropout, use_fcn=use_fcn, gpu_ids=gpu_ids)
+    elif which_model_netG == 'dcgan':
+        netG = DCGANGenerator(gpu_ids=gpu_ids, nz=noise_nc, nc=input_nc, ngf=ngf)
     else:
         raise NotImplementedError('Generator model name [%s] is not recognized' % which_model_netG)
     _to_device(netG, gpu_ids)
@@ -123,13 +130,15 @@ def define_D(input_nc, ndf, which_model_netD, n_layers_D=3, norm='batch', use_si
     elif which_model_netD == 'n_layers':
         netD = NLayerDiscriminator(input_nc, ndf, n_layers=n_layers_D, norm_layer=norm_layer, use_sigmoid=use_sigmoid,
                                    scale_factor=scale_factor, num_classes=num_classes, gpu_ids=gpu_ids)
-    elif which_model_netD in ('n_layers_sep', 'dcgan'):
-        raise NotImplementedError('Discriminator model name [%s] exists in the reference but is outside the B200 hot '
-                                  'path (basic, n_layers)' % which_model_netD)
+    elif which_model_netD == 'n_layers_sep':
+        netD = NLayerDiscriminatorSep(input_nc, ndf, n_layers=n_layers_D, norm_layer=norm_layer, use_sigmoid=use_sigmoid,
+                                      scale_factor=scale_factor, num_classes=num_classes, gpu_ids=gpu_ids)
+    elif which_model_netD == 'dcgan':
+        netD = DCGANDiscriminator(gpu_ids=gpu_ids, nc=input_nc, ndf=ndf)
     else:
         raise NotImplementedError('Discriminator model name [%s] is not recognized' % which_model_netD)
     netD.apply(weights_init)
-    if scale_factor > 1:
+    if scale_factor > 1 and getattr(netD, 'gauss_filter', None) is not None:
         for param in netD.gauss_filter.parameters():
             sigma = scale_factor // 2  # Python-2 integer division in the reference (networks.py:127)
             kw = 4 * sigma + 1
@@ -219,10 +228,10 @@ class ConvTranspose2d(nn.ConvTranspose2d):
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)
         k, s, p = self.kernel_size, self.stride, self.padding
-        if k[0] != k[1] or s[0] != s[1] or p[0] != p[1] or self.dilation != (1, 1) or self.groups != 1 or \
-                self.output_padding != (0, 0):
-            raise NotImplementedError("ConvTranspose2d: only square kernels, groups=1, dilation=1, output_padding=0")
-        self._cfg = ops.ConvCfg(True, int(k[0]), int(s[0]), int(p[0]))
+        op = self.output_padding
+        if k[0] != k[1] or s[0] != s[1] or p[0] != p[1] or self.dilation != (1, 1) or self.groups != 1 or op[0] != op[1]:
+            raise NotImplementedError("ConvTranspose2d: only square kernels / strides / paddings, groups=1, dilation=1")
+        self._cfg = ops.ConvCfg(True, int(k[0]), int(s[0]), int(p[0]), int(op[0]))
 
     def run(self, x, act="none", slope=0.2, bias_feeds_norm=False):
         return ops.conv(x, self.weight, self.bias, self._cfg, act, slope, bias_feeds_norm)
@@ -268,6 +277,19 @@ class Dropout(nn.Dropout):
         N, H, W, C = x.shape
         mask = torch.nn.functional.dropout(torch.ones((N, C, H, W), dtype=torch.float32, device=x.device), self.p, True)
         return ops.mul_mask(x, ops.to_nhwc(mask))
+
+    def forward(self, x):
+        return ops.to_nchw(self.run(ops.to_nhwc(x)))
+
+
+class ReflectionPad2d(nn.ReflectionPad2d):
+    def run(self, x):
+        p = self.padding
+        if isinstance(p, (tuple, list)):
+            if len(set(p)) != 1:
+                raise NotImplementedError("ReflectionPad2d: only the same padding on all four sides")
+            p = p[0]
+        return ops.reflection_pad(x, int(p))
 
     def forward(self, x):
         return ops.to_nchw(self.run(ops.to_nhwc(x)))
@@ -338,7 +360,7 @@ def _run_sequence(mods, x, final_act=None):
             ak = _act_kind(m)
             x = ops.activation(x, ak[0], ak[1])
             i += 1
-        elif isinstance(m, (Dropout, Upsample, AvgPool2d)):
+        elif isinstance(m, (Dropout, Upsample, AvgPool2d, ReflectionPad2d)):
             x = m.run(x)
             i += 1
         elif hasattr(m, "_fwd"):
@@ -389,6 +411,265 @@ class CycleBCELoss(nn.Module):
 
     def __call__(self, x, t):
         return ops.bce_pair_loss(x, t)
+
+
+class GANLossMultiClass(nn.Module):
+    # networks.py:188-202: CrossEntropyLoss of the per-pixel class logits against one constant class (no target tensor here)
+    def __init__(self, use_lsgan=False, num_classes=3, use_gpu=False):
+        super(GANLossMultiClass, self).__init__()
+        assert (use_lsgan is False)
+        self.num_classes = num_classes
+
+    def __call__(self, input, target_label):
+        if input.shape[1] != self.num_classes:
+            raise RuntimeError("GANLossMultiClass: %d logit channels, %d classes" % (input.shape[1], self.num_classes))
+        return ops.ce_const_loss(input, int(target_label))
+
+
+class ResnetBlock(nn.Module):
+    # networks.py:272-311
+    def __init__(self, dim, padding_type, norm_layer, use_dropout):
+        super(ResnetBlock, self).__init__()
+        self.conv_block = self.build_conv_block(dim, padding_type, norm_layer, use_dropout)
+
+    def build_conv_block(self, dim, padding_type, norm_layer, use_dropout):
+        conv_block = []
+        p = 0
+        if padding_type == 'reflect':
+            conv_block += [ReflectionPad2d(1)]
+        elif padding_type == 'zero':
+            p = 1
+        else:
+            raise NotImplementedError('padding [%s] is not implemented' % padding_type)
+        conv_block += [Conv2d(dim, dim, kernel_size=3, padding=p), norm_layer(dim), ReLU(True)]
+        if use_dropout:
+            conv_block += [Dropout(0.5)]
+        p = 0
+        if padding_type == 'reflect':
+            conv_block += [ReflectionPad2d(1)]
+        elif padding_type == 'zero':
+            p = 1
+        conv_block += [Conv2d(dim, dim, kernel_size=3, padding=p), norm_layer(dim)]
+        return nn.Sequential(*conv_block)
+
+    def _fwd(self, x):
+        return ops.add_residual(x, _run_sequence(self.conv_block, x))
+
+    def forward(self, x):
+        return ops.to_nchw(self._fwd(ops.to_nhwc(x)))
+
+
+class ResnetGenerator(nn.Module):
+    # networks.py:221-268
+    def __init__(self, input_nc, output_nc, ngf=64, norm_layer=BatchNorm2d, use_dropout=False, n_blocks=6,
+                 padding_type='reflect', use_residual=False, gpu_ids=[]):
+        assert (n_blocks >= 0)
+        super(ResnetGenerator, self).__init__()
+        self.input_nc, self.output_nc, self.ngf = input_nc, output_nc, ngf
+        self.gpu_ids = gpu_ids
+        self.use_residual = use_residual
+        model = [ReflectionPad2d(3), Conv2d(input_nc, ngf, kernel_size=7, padding=0), norm_layer(ngf), ReLU(True)]
+        n_downsampling = 2
+        for i in range(n_downsampling):
+            mult = 2 ** i
+            model += [Conv2d(ngf * mult, ngf * mult * 2, kernel_size=3, stride=2, padding=1), norm_layer(ngf * mult * 2), ReLU(True)]
+        mult = 2 ** n_downsampling
+        for i in range(n_blocks):
+            model += [ResnetBlock(ngf * mult, padding_type=padding_type, norm_layer=norm_layer, use_dropout=use_dropout)]
+        for i in range(n_downsampling):
+            mult = 2 ** (n_downsampling - i)
+            model += [ConvTranspose2d(ngf * mult, int(ngf * mult / 2), kernel_size=3, stride=2, padding=1, output_padding=1),
+                      norm_layer(int(ngf * mult / 2)), ReLU(True)]
+        model += [ReflectionPad2d(3)]
+        model += [Conv2d(ngf, output_nc, kernel_size=7, padding=0)]
+        if not use_residual:
+            model += [Tanh()]
+        self.model = nn.Sequential(*model)
+
+    def forward(self, x):
+        xn = ops.to_nhwc(x)
+        y = _run_sequence(self.model, xn)
+        if self.use_residual:
+            y = ops.add_residual(xn, y)
+        return ops.to_nchw(ops.activation(y, "tanh"))      # the reference applies Tanh again on top of the Sequential's own
+
+
+class AutoEncoder(nn.Module):
+    # networks.py:422-490
+    def __init__(self, input_nc, output_nc, n_layers=3, ngf=64, norm_layer=BatchNorm2d, use_dropout=False, gpu_ids=[]):
+        super(AutoEncoder, self).__init__()
+        self.gpu_ids = gpu_ids
+        nf_mult = 1
+        sequence = [Conv2d(input_nc, ngf, kernel_size=4, stride=2, padding=1, bias=True), norm_layer(ngf), ReLU(True)]
+        for n in range(1, n_layers):
+            nf_mult_prev = nf_mult
+            nf_mult = min(2 ** n, 8)
+            sequence += [Conv2d(nf_mult_prev * ngf, ngf * nf_mult, kernel_size=4, stride=2, padding=1, bias=True),
+                         norm_layer(ngf * nf_mult)]
+            if use_dropout:
+                sequence += [Dropout(0.2)]
+            sequence += [ReLU(True)]
+        latent_nc = min(2 ** n_layers, 8)
+        sequence += [Conv2d(nf_mult * ngf, latent_nc, kernel_size=4, stride=2, padding=1, bias=False)]
+        nf_mult = min(2 ** (n_layers - 1), 8)
+        sequence += [ConvTranspose2d(latent_nc, ngf * nf_mult, kernel_size=4, stride=2, padding=1, bias=False),
+                     norm_layer(ngf * nf_mult), ReLU(True)]
+        for n in range(1, n_layers):
+            nf_mult_prev = nf_mult
+            nf_mult = min(2 ** (n_layers - n - 1), 8)
+            sequence += [ConvTranspose2d(ngf * nf_mult_prev, ngf * nf_mult, kernel_size=4, stride=2, padding=1),
+                         norm_layer(ngf * nf_mult)]
+            if use_dropout:
+                sequence += [Dropout(0.5)]
+            sequence += [ReLU(True)]
+        sequence += [ConvTranspose2d(ngf, output_nc, kernel_size=4, stride=2, padding=1, bias=False)]
+        self.model = nn.Sequential(*sequence)
+
+    def forward(self, x, noise=None, activation=nn.Tanh()):
+        return _apply_activation(lambda ak: _run_sequence(self.model, ops.to_nhwc(x), ak), activation)
+
+
+class FCGANGeneratorStar(nn.Module):
+    # networks.py:543-639: two coupled deconv towers; tower b sees tower a's features at every level
+    def __init__(self, noise_nc, input_nc, ngf=64, n_layers=3, norm_layer=BatchNorm2d, use_dropout=False, use_fcn=False,
+                 gpu_ids=[]):
+        super(FCGANGeneratorStar, self).__init__()
+        self.gpu_ids = gpu_ids
+        self.noise_nc = int(noise_nc / 2)
+        assert (n_layers == 5)
+        assert (use_fcn is True)
+        assert (input_nc == 2)
+        input_nc = 1
+
+        def block(cin, cout, last=False):
+            mods = [ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1, bias=False)]
+            if not last:
+                mods += [norm_layer(cout), ReLU(True)]
+            return nn.Sequential(*mods)
+        widths = [ngf * 8, ngf * 8, ngf * 4, ngf * 2, ngf * 1]
+        self.conv0a = block(self.noise_nc, widths[0])
+        self.conv1a = block(widths[0], widths[1])
+        self.conv2a = block(widths[1], widths[2])
+        self.conv3a = block(widths[2], widths[3])
+        self.conv4a = block(widths[3], widths[4])
+        self.conv5a = block(widths[4], input_nc, last=True)
+        self.conv0b = block(self.noise_nc, widths[0])
+        self.conv1b = block(widths[0] * 2, widths[1])
+        self.conv2b = block(widths[1] * 2, widths[2])
+        self.conv3b = block(widths[2] * 2, widths[3])
+        self.conv4b = block(widths[3] * 2, widths[4])
+        self.conv5b = block(widths[4] * 2, input_nc, last=True)
+
+    def forward(self, noise, activation=nn.Tanh()):
+        noise1 = ops.to_nhwc(noise.narrow(1, 0, self.noise_nc).contiguous())
+        noise2 = ops.to_nhwc(noise.narrow(1, self.noise_nc, self.noise_nc).contiguous())
+
+        def run(ak):
+            hb = _run_sequence(self.conv0b, noise1)
+            ha = _run_sequence(self.conv0a, noise2)
+            for i in range(1, 6):
+                hb = _run_sequence(getattr(self, 'conv%db' % i), ops.concat_channels(ha, hb))
+                ha = _run_sequence(getattr(self, 'conv%da' % i), ha)
+            y = ops.concat_channels(ha, hb)
+            return ops.activation(y, ak[0], ak[1]) if ak is not None else y
+        return _apply_activation(run, activation)
+
+
+class NLayerDiscriminatorSep(nn.Module):
+    # networks.py:851-942.  The two input groups (channels 0-1 / channel 2) go through netA / netB as on the reference's GPU
+    # path (:930-931); its CPU path sends the 1-channel group through netA (:934), which cannot run.
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=BatchNorm2d, use_sigmoid=False, scale_factor=1,
+                 num_classes=2, gpu_ids=[]):
+        super(NLayerDiscriminatorSep, self).__init__()
+        self.gpu_ids = gpu_ids
+        self.gauss_filter = None
+        self.scale_factor = int(scale_factor)
+        kw = 4
+        padw = int(np.ceil((kw - 1) / 2))
+        logit_nc = 1 if num_classes == 2 else num_classes
+        n_sep = 2
+        assert (input_nc == 3)
+        if scale_factor > 1:
+            sigma_ = self.scale_factor // 2
+            kw_ = int(4 * sigma_ + 1)
+            self.gauss_filter = nn.Sequential(Conv2d(input_nc, input_nc, kernel_size=kw_, stride=1, padding=2 * sigma_, bias=False),
+                                              AvgPool2d(kernel_size=1, stride=self.scale_factor))
+
+        def tower(cin):
+            seq = [Conv2d(cin, ndf, kernel_size=kw, stride=2, padding=padw), LeakyReLU(0.2, False)]
+            nf_mult = 1
+            for n in range(1, n_sep):
+                nf_mult_prev = nf_mult
+                nf_mult = min(2 ** n, 8)
+                seq += [Conv2d(ndf * nf_mult_prev, ndf * nf_mult, kernel_size=kw, stride=2, padding=padw),
+                        norm_layer(ndf * nf_mult), LeakyReLU(0.2, False)]
+            return nn.Sequential(*seq), nf_mult
+        self.netA, nf_mult = tower(2)
+        self.netB, nf_mult = tower(1)
+        nf_mult = 2 * nf_mult
+        sequence = []
+        for n in range(n_sep, n_layers):
+            nf_mult_prev = nf_mult
+            nf_mult = min(2 ** n, 8)
+            sequence += [Conv2d(ndf * nf_mult_prev, ndf * nf_mult, kernel_size=kw, stride=2, padding=padw),
+                         norm_layer(ndf * nf_mult), LeakyReLU(0.2, False)]
+        nf_mult_prev = nf_mult
+        nf_mult = min(2 ** n_layers, 8)
+        sequence += [Conv2d(ndf * nf_mult_prev, ndf * nf_mult, kernel_size=kw, stride=1, padding=padw),
+                     norm_layer(ndf * nf_mult), LeakyReLU(0.2, False)]
+        sequence += [Conv2d(ndf * nf_mult, logit_nc, kernel_size=kw, stride=1, padding=padw)]
+        if use_sigmoid:
+            sequence += [Sigmoid()]
+        self.model = nn.Sequential(*sequence)
+        self._taps = None
+
+    def _gauss_taps(self):
+        return NLayerDiscriminator._gauss_taps(self)
+
+    def _fwd(self, x):
+        if self.gauss_filter is not None:
+            k = self.gauss_filter[0].kernel_size[0]
+            x = ops.gauss_decimate(x, self._gauss_taps(), k, self.scale_factor)
+        x_A, x_B = ops.split_channels(x, 2)
+        y = ops.concat_channels(_run_sequence(self.netA, x_A), _run_sequence(self.netB, x_B))
+        return _run_sequence(self.model, y)
+
+    def forward(self, x):
+        return ops.to_nchw(self._fwd(ops.to_nhwc(x)))
+
+    def forward_nhwc(self, x_nhwc):
+        return ops.to_nchw(self._fwd(x_nhwc))
+
+
+class DCGANGenerator(nn.Module):
+    # networks.py:1015-1071
+    def __init__(self, gpu_ids=[], nz=100, nc=3, ngf=64):
+        super(DCGANGenerator, self).__init__()
+        self.ngpu = len(gpu_ids)
+        seq = [ConvTranspose2d(nz, ngf * 8, 4, 1, 0, bias=False), BatchNorm2d(ngf * 8), ReLU(True)]
+        for cin, cout in ((ngf * 8, ngf * 4), (ngf * 4, ngf * 2), (ngf * 2, ngf), (ngf, int(ngf / 2))):
+            seq += [ConvTranspose2d(cin, cout, 4, 2, 1, bias=False), BatchNorm2d(cout), ReLU(True)]
+        seq += [ConvTranspose2d(int(ngf / 2), nc, 4, 2, 1, bias=False), Tanh()]
+        self.model = nn.Sequential(*seq)
+
+    def forward(self, input):
+        return ops.to_nchw(_run_sequence(self.model, ops.to_nhwc(input)))
+
+
+class DCGANDiscriminator(nn.Module):
+    # networks.py:1074-1130
+    def __init__(self, gpu_ids=[], nc=3, ndf=64):
+        super(DCGANDiscriminator, self).__init__()
+        self.ngpu = len(gpu_ids)
+        seq = [Conv2d(nc, int(ndf / 2), 4, 2, 1, bias=False), LeakyReLU(0.2, True)]
+        for cin, cout in ((int(ndf / 2), ndf), (ndf, ndf * 2), (ndf * 2, ndf * 4), (ndf * 4, ndf * 8)):
+            seq += [Conv2d(cin, cout, 4, 2, 1, bias=False), BatchNorm2d(cout), LeakyReLU(0.2, True)]
+        seq += [Conv2d(ndf * 8, 1, 4, 1, 0, bias=False), Sigmoid()]
+        self.model = nn.Sequential(*seq)
+
+    def forward(self, input):
+        output = ops.to_nchw(_run_sequence(self.model, ops.to_nhwc(input)))
+        return output.view(-1, 1).squeeze(1)
 
 
 class FCGANGenerator(nn.Module):

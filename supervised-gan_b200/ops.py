@@ -230,16 +230,18 @@ def _ws(nbytes, device):
 class ConvCfg:
     """Static description of one conv layer + its packed-weight cache."""
 
-    def __init__(self, transposed, k, stride, pad):
-        self.transposed, self.k, self.stride, self.pad = int(transposed), k, stride, pad
+    def __init__(self, transposed, k, stride, pad, out_pad=0):
+        self.transposed, self.k, self.stride, self.pad, self.out_pad = int(transposed), k, stride, pad, int(out_pad)
+        if self.out_pad and (not self.transposed or not 0 <= self.out_pad < stride):
+            raise NotImplementedError("output_padding must be in [0, stride) and belongs to ConvTranspose2d")
         self._packed = {}
 
     def desc(self, x_shape, weight):
         N, H, W, C = x_shape
         if self.transposed:
             cin, cout = weight.shape[0], weight.shape[1]
-            Ho = (H - 1) * self.stride - 2 * self.pad + self.k
-            Wo = (W - 1) * self.stride - 2 * self.pad + self.k
+            Ho = (H - 1) * self.stride - 2 * self.pad + self.k + self.out_pad
+            Wo = (W - 1) * self.stride - 2 * self.pad + self.k + self.out_pad
         else:
             cout, cin = weight.shape[0], weight.shape[1]
             Ho = (H + 2 * self.pad - self.k) // self.stride + 1
@@ -742,7 +744,99 @@ def avgpool(x, k):
     return _AvgPool.apply(x, k)
 
 
+class _ReflectionPad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        x = _chk(x, "input")
+        N, H, W, C = x.shape
+        y = torch.empty((N, H + 2 * p, W + 2 * p, C), dtype=torch.float32, device=x.device)
+        L.check(L.load().sgk_reflection_pad_fwd(_p(x), _p(y), N, C, H, W, p, _stream()), "reflection_pad_fwd")
+        ctx.args = (x.shape, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, p = ctx.args
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        dy = _chk(dy, "grad")
+        N, H, W, C = shape
+        dx = torch.empty(shape, dtype=torch.float32, device=dy.device)
+        L.check(L.load().sgk_reflection_pad_bwd(_p(dy), _p(dx), N, C, H, W, p, _stream()), "reflection_pad_bwd")
+        return dx, None
+
+
+def reflection_pad(x, p):
+    """nn.ReflectionPad2d(p) on an NHWC tensor."""
+    return _ReflectionPad.apply(x, int(p))
+
+
+class _Split2(torch.autograd.Function):
+    """(x[..., :Ca], x[..., Ca:]) of an NHWC tensor; the backward concatenates (missing halves are zero)."""
+
+    @staticmethod
+    def forward(ctx, x, Ca):
+        x = _chk(x, "input")
+        C = x.shape[3]
+        a = torch.empty(x.shape[:3] + (Ca,), dtype=torch.float32, device=x.device)
+        b = torch.empty(x.shape[:3] + (C - Ca,), dtype=torch.float32, device=x.device)
+        L.check(L.load().sgk_split2_nhwc(_p(x), _p(a), Ca, _p(b), C - Ca, x.numel() // C, _stream()), "split2")
+        ctx.c = (Ca, C - Ca)
+        return a, b
+
+    @staticmethod
+    def backward(ctx, da, db):
+        Ca, Cb = ctx.c
+        ref = da if da is not None else db
+        da = _chk(da) if da is not None else torch.zeros(ref.shape[:3] + (Ca,), dtype=torch.float32, device=ref.device)
+        db = _chk(db) if db is not None else torch.zeros(ref.shape[:3] + (Cb,), dtype=torch.float32, device=ref.device)
+        dx = torch.empty(ref.shape[:3] + (Ca + Cb,), dtype=torch.float32, device=ref.device)
+        L.check(L.load().sgk_concat2_nhwc(_p(da), Ca, _p(db), Cb, _p(dx), dx.numel() // (Ca + Cb), _stream()), "concat2")
+        return dx, None
+
+
+def split_channels(x, Ca):
+    return _Split2.apply(x, int(Ca))
+
+
+def tensor2im(image_tensor):
+    """util.tensor2im (util/util.py:15-25): first image of an NCHW batch -> uint8 numpy [H, W, 3]; the conversion runs on the
+    device, only the uint8 image crosses PCIe."""
+    x = _chk(image_tensor.detach()[0], "image")
+    C, H, W = x.shape
+    out = torch.empty((H, W, 3), dtype=torch.uint8, device=x.device)
+    L.check(L.load().sgk_tensor2im_u8(_p(x), out.data_ptr(), C, H, W, _stream()), "tensor2im")
+    return out.cpu().numpy()
+
+
 # ------------------------------------------------------------------------------------------ losses
+class _CEConstFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target):
+        lib = L.load()
+        x = _chk(x, "logits")
+        N, C, H, W = x.shape
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x)
+        ws = _ws(lib.sgk_loss_workspace_bytes(x.numel()), x.device)
+        L.check(lib.sgk_ce_const_loss(_p(x), N, C, H * W, int(target), _p(out), _p(grad), _p(ws), ws.numel(), _stream()), "ce_const_loss")
+        ctx.save_for_backward(grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        gout = _chk(gout, "loss grad")
+        out = torch.empty_like(grad)
+        L.check(L.load().sgk_scale_by_dev_scalar(_p(grad), _p(gout), _p(out), grad.numel(), _stream()), "scale")
+        return out, None
+
+
+def ce_const_loss(logits_nchw, target_class):
+    """CrossEntropyLoss of NCHW logits against one constant class (GANLossMultiClass, networks.py:188-202)."""
+    return _CEConstFn.apply(logits_nchw, int(target_class))
+
+
 class _LossFn(torch.autograd.Function):
     """kind: 'gan' (mode, target), 'l1' (y, w), 'bce_pair' (t).  Forward computes value and d/dx in one pass."""
 

@@ -113,3 +113,26 @@ def test_cpu_input_fails_loudly(built):
     D = built.networks.define_D(2, 8, "n_layers", n_layers_D=3, norm="instance", use_sigmoid=True, gpu_ids=[])
     with pytest.raises(RuntimeError, match="CUDA"):
         D(torch.zeros(1, 2, 32, 32))
+
+
+def test_remaining_architectures_have_reference_state_dict_layout():
+    """define_G / define_D of the architectures added for SURVEY 8f rank 4 expose the reference's state_dict keys and shapes
+    (fixtures written by oracle/gen_golden_f4.py from the unmodified reference)."""
+    import numpy as np
+    import supervised_gan_b200 as S
+    nw = S.networks
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    cases = {
+        "f4_resnet6": lambda: nw.define_G(2, 1, 4, "resnet_6blocks", "instance", False, gpu_ids=[]),
+        "f4_resnet9_res": lambda: nw.define_G(2, 2, 4, "resnet_9blocks", "instance", False, use_residual=True, gpu_ids=[]),
+        "f4_autoencoder": lambda: nw.define_G(2, 1, 4, "autoencoder", "instance", False, n_layers_G=3, gpu_ids=[]),
+        "f4_fcgan_star": lambda: nw.define_G(2, 0, 4, "fcgan_star", "instance", False, n_layers_G=5, use_fcn=True, noise_nc=8, gpu_ids=[]),
+        "f4_dcgan_G": lambda: nw.define_G(3, 0, 8, "dcgan", "instance", False, noise_nc=8, gpu_ids=[]),
+        "f4_dcgan_D": lambda: nw.define_D(3, 8, "dcgan", gpu_ids=[]),
+        "f4_nlayersep_s2": lambda: nw.define_D(3, 4, "n_layers_sep", n_layers_D=3, norm="instance", use_sigmoid=True, scale_factor=2, gpu_ids=[]),
+    }
+    for name, make in cases.items():
+        g = np.load(os.path.join(gdir, name + ".npz"))
+        ref = {k[3:]: g[k].shape for k in g.files if k.startswith("sd.")}
+        ours = {k: tuple(v.shape) for k, v in make().state_dict().items()}
+        assert ours == ref, name
