@@ -341,10 +341,30 @@ class FCGANModel(object):
                             ('D_fake', float(self.loss_D_fake))])
 
     def get_current_visuals(self, save_real=False, save_as_single_image=True):
+        """fcgan_model.py:201-222: uint8 [H, W, 3] images of the first sample; the (x + 1) / 2 * 255 conversion and the channel
+        padding of util.tensor2im run on the device (ops.tensor2im), only uint8 pixels are copied to the host."""
+        def im(t, idx=None):
+            t = t.detach()
+            if idx is not None:
+                t = t.index_select(1, torch.as_tensor(idx, dtype=torch.long, device=t.device))
+            return ops.tensor2im(t)
         out = OrderedDict()
+        two = len(self.chnl_idx_visual) == 2
         if self.isTrain or save_real:
-            out['real'] = self.real.detach()
-        out['fake'] = self.fake.detach()
+            if two:
+                out['real_label'] = im(self.real, self.chnl_idx_visual[0])
+                out['real_image'] = im(self.real, self.chnl_idx_visual[1])
+            else:
+                out['real'] = im(self.real)
+        if two:
+            out['fake_label'] = im(self.fake, self.chnl_idx_visual[0])
+            out['fake_image'] = im(self.fake, self.chnl_idx_visual[1])
+        else:
+            out['fake'] = im(self.fake)
+        if two and (self.isTrain or save_real):
+            out = OrderedDict((k, out[k]) for k in ('real_label', 'real_image', 'fake_label', 'fake_image'))
+        elif self.isTrain or save_real:
+            out = OrderedDict((k, out[k]) for k in ('real', 'fake'))
         return out
 
     def save_network(self, network, network_label, epoch_label, gpu_ids=[], model_dir=''):

@@ -99,3 +99,28 @@ def test_reflection_pad_matches_torch(S):
         y.backward(gy.permute(0, 2, 3, 1).contiguous())
         assert torch.equal(y.permute(0, 3, 1, 2), yr)
         assert (xn.grad.permute(0, 3, 1, 2) - xr.grad).abs().max() <= 1e-5
+
+
+def test_inference_sampler_visuals(S, tmp_path):
+    """test.py:40-49 for the fcgan model: save a trained-for-one-step model, reload it with isTrain=False, model.test(), and
+    get_current_visuals() -> util.tensor2im images (numpy restatement of util/util.py:15-25 as the checker)."""
+    from tests.test_gpu_step import make_opt
+    from supervised_gan_b200.fcgan_model import FCGANModel
+    torch.manual_seed(3)
+    kw = dict(which_channel="r_g", ngf=8, ndf=8, noiseSize=2, fineSize=128, scale_factor=[1, 2], lambda_D=[0.6, 0.4],
+              n_layers_D=[3, 3], checkpoints_dir=str(tmp_path), name="s", pool_size=0)
+    m = FCGANModel(); m.initialize(make_opt(**kw))
+    m.set_input({"A": torch.rand(1, 3, 128, 128) * 2 - 1, "A_paths": ["x"]})
+    m.optimize_parameters()
+    vis = m.get_current_visuals()
+    assert list(vis) == ["real_label", "real_image", "fake_label", "fake_image"]
+    m.save("latest")
+    t = FCGANModel(); t.initialize(make_opt(isTrain=False, **kw))
+    t.test()
+    vis = t.get_current_visuals()
+    assert list(vis) == ["fake_label", "fake_image"]
+    fake = t.fake.detach().cpu().numpy()
+    for k, c in (("fake_label", 0), ("fake_image", 1)):
+        ref = ((fake[0, c:c + 1] + 1) / 2.0 * 255.0).repeat(3, 0)
+        ref = np.transpose(ref, (1, 2, 0)).astype(np.uint8)
+        assert vis[k].dtype == np.uint8 and vis[k].shape == (128, 128, 3) and np.array_equal(vis[k], ref)
