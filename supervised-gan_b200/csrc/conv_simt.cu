@@ -1062,6 +1062,7 @@ int conv_fwd_tc(const SgkConvDesc* d, const GatherPlan& g, const float* in, cons
 int conv_wgrad_tc(const SgkConvDesc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t st);
 size_t conv_wgrad_tc_workspace_bytes(const SgkConvDesc* d);
+int edge_wgrad_ctas_per_group();   // conv_tc.cu
 int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* part, int ctas, const float* y, int act, float slope,
                    float* bias_part, cudaStream_t st);
 int launch_colsum_final(const float* part, float* out, int C, int chunks, cudaStream_t st);
@@ -1124,7 +1125,7 @@ extern "C" int sgk_conv_wgrad_act(const SgkConvDesc* d, const float* x, const fl
   const int K = e.k * e.k * e.I;
   const long long ntiles = (long long)ceil_div(e.Ws, EG_TW) * ceil_div(e.Hs, EG_TH) * e.N;
   const int cgroups = ceil_div(e.O, 32);
-  long long ctas = 3LL * sm_count() / cgroups;
+  long long ctas = (long long)edge_wgrad_ctas_per_group() / cgroups;
   if (ctas < 1) ctas = 1;
   if (ctas > ntiles) ctas = ntiles;
   const size_t need = (size_t)ctas * e.O * (K + 1) * sizeof(float);
@@ -1162,7 +1163,7 @@ extern "C" int sgk_conv_wgrad(const SgkConvDesc* d, const float* x, const float*
     const int tiles_x = ceil_div(e.Ws, EG_TW), tiles_y = ceil_div(e.Hs, EG_TH);
     long long ntiles = (long long)tiles_x * tiles_y * e.N;
     const int cgroups = ceil_div(e.O, 32);
-    long long ctas = (ekey == 408 ? 3LL : 2LL) * sm_count() / cgroups;
+    long long ctas = (ekey == 408 ? (long long)edge_wgrad_ctas_per_group() : 2LL * sm_count()) / cgroups;
     if (ctas < 1) ctas = 1;
     if (ctas > ntiles) ctas = ntiles;
     const size_t need_e = (size_t)ctas * e.O * K * sizeof(float);

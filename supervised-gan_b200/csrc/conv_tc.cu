@@ -2131,6 +2131,144 @@ edge_wgrad_tma_kernel(const __grid_constant__ EdgeWParams p, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------ outer-product variant
+// Same problem, register-blocked: the kernel above keeps lane = G channel and reads 32 broadcast x values per pixel (8 LDS.128
+// for 32 FFMA per thread: the shared-memory pipe, not the FMA pipe, was the limit -- 17 TFLOP/s).  Here 16 threads share one
+// pixel: thread (co8, a) owns the 8 x 8 block (8 output channels) x (tap row a: 4 taps x 2 image channels) and per pixel loads
+// 8 G values + 8 x values (4 LDS.128) for 64 FFMA; a warp streams two pixels at a time, 16 warps = 32 pixel streams.  G (and,
+// fused, the activated output y) tiles arrive by TMA next to the x patch, out-of-range pixels zero-filled, so the inner loop
+// has no bounds checks; the activation backward and the bias sums are a pre-pass over the G tile in shared memory.
+struct alignas(64) EdgeOpMaps {
+  CUtensorMap x, g, y;
+};
+
+template <int S, bool FUSED>
+__global__ void __launch_bounds__(512, 1)
+edge_wgrad_op_kernel(const __grid_constant__ EdgeWParams p, const __grid_constant__ EdgeOpMaps maps) {
+  constexpr int ROWF = ((EW_TW - 1) * S + 4) * 2;
+  constexpr uint32_t G_BYTES = EW_TH * EW_TW * 32 * 4;                 // 32 KB: 256 pixels x 32 channels
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 127u) & ~127u;
+  uint8_t* gen = smem_raw + (base - raw_u32);
+  const uint32_t stage_bytes = p.buf_stride + G_BYTES * (FUSED ? 2u : 1u);
+  const uint32_t red_bytes = 32u * 1024u * 4u;                           // final reduction: 32 pixel streams x (32 x 32) floats
+  const uint32_t bar0 = base + (2u * stage_bytes > red_bytes ? 2u * stage_bytes : red_bytes);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int ntiles = per_img * p.N;
+  const uint32_t tx_bytes = (uint32_t)p.PH * (uint32_t)p.rowf * 4u + G_BYTES * (FUSED ? 2u : 1u);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8u, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t, int buf) {
+    const int n = t / per_img;
+    const int r2 = t - n * per_img;
+    const int tyi = r2 / p.tiles_x, txi = r2 - tyi * p.tiles_x;
+    const uint32_t bar = bar0 + 8u * (uint32_t)buf, dst = base + (uint32_t)buf * stage_bytes;
+    mbar_arrive_expect_tx(bar, tx_bytes);
+    tma_load_3d(dst, &maps.x, (txi * EW_TW * p.s + p.off) * p.Cx, tyi * EW_TH * p.s + p.off, n, bar);
+    tma_load_4d(dst + p.buf_stride, &maps.g, (int)blockIdx.y * 32, txi * EW_TW, tyi * EW_TH, n, bar);
+    if constexpr (FUSED) tma_load_4d(dst + p.buf_stride + G_BYTES, &maps.y, (int)blockIdx.y * 32, txi * EW_TW, tyi * EW_TH, n, bar);
+  };
+  const int half = lane >> 4, t16 = lane & 15;
+  const int co8 = t16 >> 2, a = t16 & 3;
+  const int stream = warp * 2 + half;                                    // 0..31: pixels stream + 32 j of the tile
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  const float neg = p.act == SGK_ACT_LRELU ? p.slope : 0.f;
+  if (tid == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (tid == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, buf ^ 1);   // consumed before the trailing barrier below
+    mbar_wait(bar0 + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));
+    const float* patch = reinterpret_cast<const float*>(gen + (uint32_t)buf * stage_bytes);
+    float* gt = reinterpret_cast<float*>(gen + (uint32_t)buf * stage_bytes + p.buf_stride);
+    if constexpr (FUSED) {
+      // dpre = dy * act'(y) in place (ReLU / LeakyReLU: the sign of y is the sign of the pre-activation) + bias column sums
+      const float* yt = gt + EW_TH * EW_TW * 32;
+#pragma unroll 4
+      for (int q = 0; q < 16; ++q) {
+        const int idx = (q * 16 + warp) * 32 + lane;
+        const float v = gt[idx] * (yt[idx] > 0.f ? 1.f : neg);
+        gt[idx] = v;
+        bsum += v;
+      }
+      __syncthreads();
+    }
+#pragma unroll 2
+    for (int j = 0; j < 8; ++j) {
+      const int px = stream + 32 * j;
+      const int oyl = px >> 5, oxl = px & 31;
+      const float* gp = gt + px * 32 + co8 * 8;
+      const float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + 4);
+      const float* xp = patch + (oyl * S + a) * ROWF + oxl * S * 2;
+      float xv[8];
+      if constexpr (S == 2) {
+        const float4 x0 = *reinterpret_cast<const float4*>(xp), x1 = *reinterpret_cast<const float4*>(xp + 4);
+        xv[0] = x0.x; xv[1] = x0.y; xv[2] = x0.z; xv[3] = x0.w; xv[4] = x1.x; xv[5] = x1.y; xv[6] = x1.z; xv[7] = x1.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 v = *reinterpret_cast<const float2*>(xp + 2 * q);
+          xv[2 * q] = v.x; xv[2 * q + 1] = v.y;
+        }
+      }
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[i][q] = fmaf(gv[i], xv[q], acc[i][q]);
+    }
+    __syncthreads();   // stage `buf` fully consumed
+  }
+  // fixed-order reduction over the 32 pixel streams through shared memory (the stage buffers are free now)
+  float* red = reinterpret_cast<float*>(gen);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int q = 0; q < 8; q += 4)
+      *reinterpret_cast<float4*>(red + stream * 1024 + (co8 * 8 + i) * 32 + a * 8 + q) =
+          make_float4(acc[i][q], acc[i][q + 1], acc[i][q + 2], acc[i][q + 3]);
+  __syncthreads();
+#pragma unroll
+  for (int o = tid; o < 1024; o += 512) {
+    float sacc = 0.f;
+#pragma unroll 8
+    for (int sidx = 0; sidx < 32; ++sidx) sacc += red[sidx * 1024 + o];
+    const int mm = blockIdx.y * 32 + (o >> 5);
+    if (mm < p.Cm) p.part[((long long)blockIdx.x * p.Cm + mm) * EW_K + (o & 31)] = sacc;
+  }
+  if constexpr (FUSED) {
+    if (p.bias_part != nullptr) {
+      __syncthreads();
+      red[warp * 32 + lane] = bsum;                                      // thread (warp, lane) summed channel `lane`
+      __syncthreads();
+      if (tid < 32) {
+        float sb = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) sb += red[w * 32 + tid];
+        const int mm = blockIdx.y * 32 + tid;
+        if (mm < p.Cm) p.bias_part[(long long)blockIdx.x * p.Cm + mm] = sb;
+      }
+    }
+  }
+}
+
+// CTAs (= partial blocks) the image-edge weight gradient uses per 32-channel group: one per SM for the outer-product kernel
+int edge_wgrad_ctas_per_group() {
+  static const int op = getenv("SGK_EDGE_OP") ? atoi(getenv("SGK_EDGE_OP")) : 1;
+  return op ? sm_count() : 3 * sm_count();
+}
+
 // returns SGK_EUNSUPPORTED when the shape / alignment does not fit (the caller keeps its own kernel)
 int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* part, int ctas, const float* y, int act, float slope,
                    float* bias_part, cudaStream_t st) {
@@ -2157,6 +2295,45 @@ int edge_wgrad_tma(const EquivConv& e, const float* g, const float* x, float* pa
   CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return SGK_EUNSUPPORTED;
+  static const int use_op = getenv("SGK_EDGE_OP") ? atoi(getenv("SGK_EDGE_OP")) : 1;
+  if (use_op && (e.O % 4) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && (y == nullptr || (reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
+    EdgeOpMaps om{};
+    om.x = xmap;
+    cuuint64_t gdim[4] = {(cuuint64_t)e.O, (cuuint64_t)e.Ws, (cuuint64_t)e.Hs, (cuuint64_t)e.N};
+    cuuint64_t gstr[3] = {(cuuint64_t)e.O * 4, (cuuint64_t)e.Ws * e.O * 4, (cuuint64_t)e.Hs * e.Ws * e.O * 4};
+    cuuint32_t gbox[4] = {32u, (cuuint32_t)EW_TW, (cuuint32_t)EW_TH, 1u};
+    cuuint32_t ges[4] = {1u, 1u, 1u, 1u};
+    CUresult r2 = encode(&om.g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g, gdim, gstr, gbox, ges, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r2 == CUDA_SUCCESS && y != nullptr)
+      r2 = encode(&om.y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)y, gdim, gstr, gbox, ges, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r2 == CUDA_SUCCESS) {
+      const bool fused = y != nullptr;
+      const size_t stage = (size_t)q.buf_stride + 32768u * (fused ? 2 : 1);
+      const size_t body = 2 * stage > 131072 ? 2 * stage : 131072;
+      const size_t smem_op = body + 16 + 128;
+      static bool attr_op = false;
+      if (!attr_op) {
+        cudaError_t ce = cudaFuncSetAttribute(edge_wgrad_op_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(edge_wgrad_op_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(edge_wgrad_op_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(edge_wgrad_op_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(edge_wgrad_op_kernel)");
+        attr_op = true;
+      }
+      dim3 grid_op((unsigned)ctas, (unsigned)ceil_div(e.O, 32));
+      if (e.s == 1) {
+        if (fused) edge_wgrad_op_kernel<1, true><<<grid_op, 512, smem_op, st>>>(q, om);
+        else edge_wgrad_op_kernel<1, false><<<grid_op, 512, smem_op, st>>>(q, om);
+      } else {
+        if (fused) edge_wgrad_op_kernel<2, true><<<grid_op, 512, smem_op, st>>>(q, om);
+        else edge_wgrad_op_kernel<2, false><<<grid_op, 512, smem_op, st>>>(q, om);
+      }
+      SGK_LAUNCH_CHECK("edge_wgrad_op_kernel");
+      return SGK_OK;
+    }
+  }
   const size_t smem = 2 * (size_t)q.buf_stride + 16 + (size_t)8 * 32 * 33 * sizeof(float) + 128;
   static bool attr = false;
   if (!attr) {
