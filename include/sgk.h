@@ -184,6 +184,10 @@ int sgk_scale_by_dev_scalar(const float* x, const float* alpha_dev, float* out, 
  * taps: [C, k, k] floats = diagonal of gauss_filter.0.weight (host checks off-diagonals are 0). */
 int sgk_gauss_decimate_fwd(const float* x, const float* taps, float* y, int N, int C, int H, int W,
                            int k, int scale, void* stream);
+/* same result for separable taps, taps[c][a][b] = v[c][a] * u[c][b] (u, v: [C][k] device arrays): one coalesced vertical sweep +
+ * one horizontal sweep per output row.  SGK_EUNSUPPORTED when a line does not fit shared memory (use the dense entry point). */
+int sgk_gauss_decimate_sep_fwd(const float* x, const float* u, const float* v, float* y, int N, int C, int H, int W, int k,
+                               int scale, void* stream);
 int sgk_gauss_decimate_bwd(const float* dy, const float* taps, float* dx, int N, int C, int H, int W,
                            int k, int scale, void* stream);
 /* nn.Upsample(scale_factor=2, mode='bilinear'), align_corners=False (networks.py:753; cgan_model.py:53) */

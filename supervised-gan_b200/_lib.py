@@ -72,6 +72,7 @@ SIGNATURES = {
     "sgk_scale_by_dev_scalar": (c_int, [P, P, P, c_size_t, P]),
     "sgk_gauss_decimate_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "sgk_gauss_decimate_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "sgk_gauss_decimate_sep_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "sgk_bilinear_up2_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "sgk_bilinear_up2_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "sgk_avgpool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),

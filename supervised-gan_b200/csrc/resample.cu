@@ -253,6 +253,81 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dy, float* __restri
   dx[i] = (oy < Ho && ox < Wo) ? __ldg(dy + (((long long)n * Ho + oy) * Wo + ox) * C + c) / (float)(k * k) : 0.f;
 }
 
+
+// Separable form of the blur + decimation (taps[c][a][b] = v[c][a] * u[c][b], which is what define_D's Gaussian is,
+// networks.py:22-40): one block per output row; a vertical sweep over the k input rows it needs -- fully coalesced float4
+// loads -- leaves the row-filtered line in shared memory, a horizontal sweep produces the kept pixels.  The dense kernel
+// above issues k*k strided 4-byte loads per output (25 % sector efficiency: it ran at 14 % of the HBM rate).
+template <int KT>   // compile-time tap count (0 = runtime): the k row loads of the vertical sweep are then issued back to back
+__global__ void __launch_bounds__(256) gauss_decimate_sep_fwd_kernel(const float* __restrict__ x, const float* __restrict__ u,
+                                                                     const float* __restrict__ v, float* __restrict__ y, int C, int H,
+                                                                     int W, int Ho, int Wo, int k_, int s) {
+  const int k = KT ? KT : k_;
+  extern __shared__ float gsm[];                 // [C*k] v taps, [C*k] u taps, then the padded line (W + 2 pad) * C
+  float* vt = gsm;
+  float* ut = gsm + C * k;
+  float* line = gsm + 2 * C * k;
+  const int pad = (k - 1) / 2;
+  const int oy = blockIdx.x, n = blockIdx.y;
+  for (int i = threadIdx.x; i < C * k; i += blockDim.x) { vt[i] = __ldg(v + i); ut[i] = __ldg(u + i); }
+  const int WC = W * C, padC = pad * C;
+  for (int i = threadIdx.x; i < padC; i += blockDim.x) { line[i] = 0.f; line[padC + WC + i] = 0.f; }
+  __syncthreads();
+  const int iy0 = oy * s - pad;
+  const float* __restrict__ xn = x + (long long)n * H * WC;
+  if ((WC & 3) == 0 && (4 % C == 0 || C % 4 == 0)) {
+    for (int i = threadIdx.x * 4; i < WC; i += blockDim.x * 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const int c0 = i % C;
+      if constexpr (KT != 0) {
+        float4 t[KT];
+#pragma unroll
+        for (int a = 0; a < KT; ++a) {
+          const int iy = iy0 + a;
+          t[a] = (iy >= 0 && iy < H) ? __ldg(reinterpret_cast<const float4*>(xn + (long long)iy * WC + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int a = 0; a < KT; ++a) {
+          acc[0] = fmaf(vt[c0 * KT + a], t[a].x, acc[0]);
+          acc[1] = fmaf(vt[((c0 + 1) % C) * KT + a], t[a].y, acc[1]);
+          acc[2] = fmaf(vt[((c0 + 2) % C) * KT + a], t[a].z, acc[2]);
+          acc[3] = fmaf(vt[((c0 + 3) % C) * KT + a], t[a].w, acc[3]);
+        }
+      } else
+      for (int a = 0; a < k; ++a) {
+        const int iy = iy0 + a;
+        if (iy < 0 || iy >= H) continue;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(xn + (long long)iy * WC + i));
+        acc[0] = fmaf(vt[c0 * k + a], t.x, acc[0]);
+        acc[1] = fmaf(vt[((c0 + 1) % C) * k + a], t.y, acc[1]);
+        acc[2] = fmaf(vt[((c0 + 2) % C) * k + a], t.z, acc[2]);
+        acc[3] = fmaf(vt[((c0 + 3) % C) * k + a], t.w, acc[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) line[padC + i + j] = acc[j];
+    }
+  } else {
+    for (int i = threadIdx.x; i < WC; i += blockDim.x) {
+      float acc = 0.f;
+      const int c = i % C;
+      for (int a = 0; a < k; ++a) {
+        const int iy = iy0 + a;
+        if (iy >= 0 && iy < H) acc = fmaf(vt[c * k + a], __ldg(xn + (long long)iy * WC + i), acc);
+      }
+      line[padC + i] = acc;
+    }
+  }
+  __syncthreads();
+  float* __restrict__ yo = y + (((long long)n * Ho + oy) * Wo) * C;
+  for (int o = threadIdx.x; o < Wo * C; o += blockDim.x) {
+    const int ox = o / C, c = o - ox * C;
+    const float* lp = line + (ox * s) * C + c;    // = padC + (ox * s - pad) * C + c
+    float acc = 0.f;
+    for (int b = 0; b < k; ++b) acc = fmaf(ut[c * k + b], lp[b * C], acc);
+    yo[o] = acc;
+  }
+}
+
 }  // namespace sgk
 using namespace sgk;
 
@@ -280,6 +355,22 @@ extern "C" int sgk_gauss_decimate_fwd(const float* x, const float* taps, float* 
   else if (C == 1 && k == 9) gauss_decimate_fwd_kernel<9, 1><<<grid, 256, 0, st>>>(x, taps, y, C, H, W, Ho, Wo, k, scale, rows_pb);
   else gauss_decimate_fwd_kernel<0, 0><<<grid, 256, 0, st>>>(x, taps, y, C, H, W, Ho, Wo, k, scale, rows_pb);
   SGK_LAUNCH_CHECK("gauss_decimate_fwd_kernel");
+  return SGK_OK;
+}
+extern "C" int sgk_gauss_decimate_sep_fwd(const float* x, const float* u, const float* v, float* y, int N, int C, int H, int W, int k,
+                                          int scale, void* stream) {
+  int rc = gauss_args(x, u, y, N, C, H, W, k, scale);
+  if (rc) return rc;
+  SGK_CHECK_ARG(v, "sgk_gauss_decimate_sep_fwd: null argument");
+  int Ho = (H + scale - 1) / scale, Wo = (W + scale - 1) / scale;
+  const size_t smem = ((size_t)2 * C * k + (size_t)(W + k - 1) * C) * sizeof(float);
+  if (smem > 48 * 1024 || N > 65535) return SGK_EUNSUPPORTED;      // the caller keeps the dense kernel
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return SGK_EUNSUPPORTED;
+  dim3 grid((unsigned)Ho, (unsigned)N);
+  if (k == 5) gauss_decimate_sep_fwd_kernel<5><<<grid, 256, smem, (cudaStream_t)stream>>>(x, u, v, y, C, H, W, Ho, Wo, k, scale);
+  else if (k == 9) gauss_decimate_sep_fwd_kernel<9><<<grid, 256, smem, (cudaStream_t)stream>>>(x, u, v, y, C, H, W, Ho, Wo, k, scale);
+  else gauss_decimate_sep_fwd_kernel<0><<<grid, 256, smem, (cudaStream_t)stream>>>(x, u, v, y, C, H, W, Ho, Wo, k, scale);
+  SGK_LAUNCH_CHECK("gauss_decimate_sep_fwd_kernel");
   return SGK_OK;
 }
 extern "C" int sgk_gauss_decimate_bwd(const float* dy, const float* taps, float* dx, int N, int C, int H, int W, int k,

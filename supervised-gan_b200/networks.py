@@ -749,13 +749,24 @@ class NLayerDiscriminator(nn.Module):
             if float(off) > 1e-12 * max(float(taps.abs().sum()), 1.0):
                 raise NotImplementedError("gauss_filter has non-zero cross-channel taps; only the channel-diagonal "
                                           "Gaussian of define_D (networks.py:125-129) has a kernel")
-            self._taps = (tag, taps)
+            # separable? (define_D's Gaussian is an outer product; a filter loaded from elsewhere may not be)
+            v, u = taps.sum(dim=2), taps.sum(dim=1)                     # [C, k] row / column marginals
+            tot = taps.sum(dim=(1, 2)).clamp_min(1e-30)
+            outer = v[:, :, None] * u[:, None, :] / tot[:, None, None]
+            sep = None
+            if float((outer - taps).abs().max()) <= 1e-6 * float(taps.abs().max()):
+                sep = ((u / tot[:, None]).contiguous(), v.contiguous())    # taps = outer(v, u / total)
+            self._taps = (tag, taps, sep)
         return self._taps[1]
+
+    def _gauss_sep(self):
+        self._gauss_taps()
+        return self._taps[2]
 
     def _fwd(self, x):
         if self.gauss_filter is not None:
             k = self.gauss_filter[0].kernel_size[0]
-            x = ops.gauss_decimate(x, self._gauss_taps(), k, self.scale_factor)
+            x = ops.gauss_decimate(x, self._gauss_taps(), k, self.scale_factor, self._gauss_sep())
         return _run_sequence(self.model, x)
 
     def forward(self, x):

@@ -666,13 +666,22 @@ def add_residual(a, b):
 # ------------------------------------------------------------------------------------------ resampling
 class _GaussDecimate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, taps, k, scale):
+    def forward(ctx, x, taps, k, scale, sep=None):
         x, taps = _chk(x, "input"), _chk(taps, "taps")
         N, H, W, C = x.shape
         Ho, Wo = (H + scale - 1) // scale, (W + scale - 1) // scale
         y = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=x.device)
-        L.check(_timed("gauss_fwd k%d s%d C%d %dx%d N%d" % (k, scale, C, H, W, N), 0.0, 4.0 * (x.numel() + y.numel()),
-                       lambda st: L.load().sgk_gauss_decimate_fwd(_p(x), _p(taps), _p(y), N, C, H, W, k, scale, st)), "gauss_fwd")
+        lib = L.load()
+
+        def run(st):
+            if sep is not None and _precision != L.FP32:
+                # separable taps (what define_D builds): coalesced two-sweep kernel; the strict fp32 mode keeps the dense
+                # kernel, whose accumulation order the golden tolerances were set with
+                rc = lib.sgk_gauss_decimate_sep_fwd(_p(x), _p(sep[0]), _p(sep[1]), _p(y), N, C, H, W, k, scale, st)
+                if rc != L.EUNSUPPORTED:
+                    return rc
+            return lib.sgk_gauss_decimate_fwd(_p(x), _p(taps), _p(y), N, C, H, W, k, scale, st)
+        L.check(_timed("gauss_fwd k%d s%d C%d %dx%d N%d" % (k, scale, C, H, W, N), 0.0, 4.0 * (x.numel() + y.numel()), run), "gauss_fwd")
         ctx.args = (x.shape, k, scale)
         ctx.save_for_backward(taps)
         return y
@@ -682,17 +691,18 @@ class _GaussDecimate(torch.autograd.Function):
         shape, k, scale = ctx.args
         (taps,) = ctx.saved_tensors
         if not ctx.needs_input_grad[0]:
-            return None, None, None, None
+            return None, None, None, None, None
         dy = _chk(dy, "grad")
         N, H, W, C = shape
         dx = torch.empty(shape, dtype=torch.float32, device=dy.device)
         L.check(_timed("gauss_bwd k%d s%d C%d %dx%d N%d" % (k, scale, C, H, W, N), 0.0, 4.0 * (dx.numel() + dy.numel()),
                        lambda st: L.load().sgk_gauss_decimate_bwd(_p(dy), _p(taps), _p(dx), N, C, H, W, k, scale, st)), "gauss_bwd")
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
-def gauss_decimate(x, taps, k, scale):
-    return _GaussDecimate.apply(x, taps, k, scale)
+def gauss_decimate(x, taps, k, scale, sep=None):
+    """sep: optional (u, v) device tensors [C, k] with taps[c] == outer(v[c], u[c]) (see NLayerDiscriminator._gauss_taps)."""
+    return _GaussDecimate.apply(x, taps, k, scale, sep)
 
 
 class _BilinearUp2(torch.autograd.Function):

@@ -222,3 +222,21 @@ def test_crn_real_width_tf32_vs_fp64(S, mode, nb):
     assert len(m) >= 10
     bad = {k: v for k, v in m.items() if not (v[0] >= 0.98 and v[1] <= 0.2)}
     assert not bad, bad
+
+
+def test_gauss_decimate_separable_matches_dense(S):
+    """tf32 mode routes define_D's separable Gaussian through the two-sweep kernel; it must agree with the dense kernel (the
+    one the fp32 golden tests pin) to fp32 rounding: <= 2e-6 of the output's max, odd sizes and both scales."""
+    from supervised_gan_b200 import networks as nw
+    for scale, (H, W) in ((2, (96, 80)), (4, (131, 77)), (4, (512, 512))):
+        D = nw.define_D(2, 4, "n_layers", n_layers_D=3, norm="instance", use_sigmoid=True, scale_factor=scale, gpu_ids=[0])
+        x = torch.randn(2, H, W, 2, device="cuda")
+        k = D.gauss_filter[0].kernel_size[0]
+        assert D._gauss_sep() is not None
+        dense = S.ops.gauss_decimate(x, D._gauss_taps(), k, scale, None)
+        sep = S.ops.gauss_decimate(x, D._gauss_taps(), k, scale, D._gauss_sep())
+        assert float((dense - sep).abs().max()) <= 2e-6 * float(dense.abs().max())
+    # a non-separable filter keeps the dense kernel
+    D.gauss_filter[0].weight.data[0, 0, 0, 1] += 0.01
+    S.ops.bump_weights_epoch()
+    assert D._gauss_sep() is None
