@@ -3,6 +3,7 @@
 //   * bilinear x2 up-sampling, align_corners=False; backward as a gather (no atomics)
 //   * k x k average pooling
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace sgk {
 
@@ -258,11 +259,9 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dy, float* __restri
 // networks.py:22-40): one block per output row; a vertical sweep over the k input rows it needs -- fully coalesced float4
 // loads -- leaves the row-filtered line in shared memory, a horizontal sweep produces the kept pixels.  The dense kernel
 // above issues k*k strided 4-byte loads per output (25 % sector efficiency: it ran at 14 % of the HBM rate).
-template <int KT>   // compile-time tap count (0 = runtime): the k row loads of the vertical sweep are then issued back to back
 __global__ void __launch_bounds__(256) gauss_decimate_sep_fwd_kernel(const float* __restrict__ x, const float* __restrict__ u,
                                                                      const float* __restrict__ v, float* __restrict__ y, int C, int H,
-                                                                     int W, int Ho, int Wo, int k_, int s) {
-  const int k = KT ? KT : k_;
+                                                                     int W, int Ho, int Wo, int k, int s) {
   extern __shared__ float gsm[];                 // [C*k] v taps, [C*k] u taps, then the padded line (W + 2 pad) * C
   float* vt = gsm;
   float* ut = gsm + C * k;
@@ -279,21 +278,6 @@ __global__ void __launch_bounds__(256) gauss_decimate_sep_fwd_kernel(const float
     for (int i = threadIdx.x * 4; i < WC; i += blockDim.x * 4) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       const int c0 = i % C;
-      if constexpr (KT != 0) {
-        float4 t[KT];
-#pragma unroll
-        for (int a = 0; a < KT; ++a) {
-          const int iy = iy0 + a;
-          t[a] = (iy >= 0 && iy < H) ? __ldg(reinterpret_cast<const float4*>(xn + (long long)iy * WC + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int a = 0; a < KT; ++a) {
-          acc[0] = fmaf(vt[c0 * KT + a], t[a].x, acc[0]);
-          acc[1] = fmaf(vt[((c0 + 1) % C) * KT + a], t[a].y, acc[1]);
-          acc[2] = fmaf(vt[((c0 + 2) % C) * KT + a], t[a].z, acc[2]);
-          acc[3] = fmaf(vt[((c0 + 3) % C) * KT + a], t[a].w, acc[3]);
-        }
-      } else
       for (int a = 0; a < k; ++a) {
         const int iy = iy0 + a;
         if (iy < 0 || iy >= H) continue;
@@ -367,9 +351,7 @@ extern "C" int sgk_gauss_decimate_sep_fwd(const float* x, const float* u, const 
   if (smem > 48 * 1024 || N > 65535) return SGK_EUNSUPPORTED;      // the caller keeps the dense kernel
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return SGK_EUNSUPPORTED;
   dim3 grid((unsigned)Ho, (unsigned)N);
-  if (k == 5) gauss_decimate_sep_fwd_kernel<5><<<grid, 256, smem, (cudaStream_t)stream>>>(x, u, v, y, C, H, W, Ho, Wo, k, scale);
-  else if (k == 9) gauss_decimate_sep_fwd_kernel<9><<<grid, 256, smem, (cudaStream_t)stream>>>(x, u, v, y, C, H, W, Ho, Wo, k, scale);
-  else gauss_decimate_sep_fwd_kernel<0><<<grid, 256, smem, (cudaStream_t)stream>>>(x, u, v, y, C, H, W, Ho, Wo, k, scale);
+  gauss_decimate_sep_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, u, v, y, C, H, W, Ho, Wo, k, scale);
   SGK_LAUNCH_CHECK("gauss_decimate_sep_fwd_kernel");
   return SGK_OK;
 }

@@ -674,7 +674,7 @@ class _GaussDecimate(torch.autograd.Function):
         lib = L.load()
 
         def run(st):
-            if sep is not None and _precision != L.FP32:
+            if sep is not None and _precision != L.FP32 and os.environ.get("SGK_GAUSS_SEP", "1") != "0":
                 # separable taps (what define_D builds): coalesced two-sweep kernel; the strict fp32 mode keeps the dense
                 # kernel, whose accumulation order the golden tolerances were set with
                 rc = lib.sgk_gauss_decimate_sep_fwd(_p(x), _p(sep[0]), _p(sep[1]), _p(y), N, C, H, W, k, scale, st)

@@ -228,7 +228,7 @@ def test_gauss_decimate_separable_matches_dense(S):
     """tf32 mode routes define_D's separable Gaussian through the two-sweep kernel; it must agree with the dense kernel (the
     one the fp32 golden tests pin) to fp32 rounding: <= 2e-6 of the output's max, odd sizes and both scales."""
     from supervised_gan_b200 import networks as nw
-    for scale, (H, W) in ((2, (96, 80)), (4, (131, 77)), (4, (512, 512))):
+    for scale, (H, W) in ((2, (96, 80)), (4, (131, 77)), (4, (512, 512)), (2, (128, 128)), (4, (128, 128)), (2, (16, 16)), (4, (64, 64))):
         D = nw.define_D(2, 4, "n_layers", n_layers_D=3, norm="instance", use_sigmoid=True, scale_factor=scale, gpu_ids=[0])
         x = torch.randn(2, H, W, 2, device="cuda")
         k = D.gauss_filter[0].kernel_size[0]
