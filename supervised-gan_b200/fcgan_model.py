@@ -336,9 +336,10 @@ class FCGANModel(object):
 
     # ------------------------------------------------------------------ reporting / checkpoints
     def get_current_errors(self):
-        # reference reads loss.data[0] (fcgan_model.py:195-199); one D2H sync per value, only when printing
-        return OrderedDict([('G_GAN', float(self.loss_G)), ('D_real', float(self.loss_D_real)),
-                            ('D_fake', float(self.loss_D_fake))])
+        # reference reads loss.data[0] three times (fcgan_model.py:195-199); here the three scalars cross in ONE 12-byte
+        # device-to-host copy (one synchronisation instead of three)
+        vals = torch.stack([self.loss_G.detach(), self.loss_D_real.detach(), self.loss_D_fake.detach()]).tolist()
+        return OrderedDict([('G_GAN', vals[0]), ('D_real', vals[1]), ('D_fake', vals[2])])
 
     def get_current_visuals(self, save_real=False, save_as_single_image=True):
         """fcgan_model.py:201-222: uint8 [H, W, 3] images of the first sample; the (x + 1) / 2 * 255 conversion and the channel
