@@ -236,6 +236,11 @@ int sgk_image_transform_u8(const uint8_t* src, int H0, int W0, int C0, float* ds
 int sgk_l1_weight_map(const float* real_a, float* weight, int N, int C, long long HW, const float* weights_host, int nw,
                       void* stream);
 
+/* the channel selection of set_input (fcgan_model.py:118-122) as ONE strided host->device copy: `rows` samples, each `width_bytes`
+ * contiguous bytes (the selected channel planes) out of `src_pitch` bytes per source sample (pinned host memory -> asynchronous). */
+int sgk_h2d_rows_async(void* dst, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t width_bytes, size_t rows,
+                       void* stream);
+
 /* ---------------------------------------------------------------- remaining architectures / inference
  * nn.ReflectionPad2d(p) on NHWC (ResnetGenerator / ResnetBlock, networks.py:238,263,282,294); x [N][H][W][C] -> y [N][H+2p][W+2p][C];
  * backward gathers the <= 2 x 2 mirrored positions per input pixel (deterministic). */

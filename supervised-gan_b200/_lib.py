@@ -83,6 +83,7 @@ SIGNATURES = {
     "sgk_bce_pair_loss": (c_int, [P, P, c_size_t, P, P, P, c_size_t, P]),
     "sgk_image_pool_query": (c_int, [P, P, P, P, c_int, ctypes.c_longlong, c_int, P]),
     "sgk_image_transform_u8": (c_int, [P, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P]),
+    "sgk_h2d_rows_async": (c_int, [P, c_size_t, P, c_size_t, c_size_t, c_size_t, P]),
     "sgk_l1_weight_map": (c_int, [P, P, c_int, c_int, ctypes.c_longlong, P, c_int, P]),
     "sgk_reflection_pad_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "sgk_reflection_pad_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),

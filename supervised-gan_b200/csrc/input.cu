@@ -238,3 +238,15 @@ extern "C" int sgk_ce_const_loss(const float* logits, int N, int C, long long HW
   SGK_LAUNCH_CHECK("ce_const_final_kernel");
   return SGK_OK;
 }
+
+// Host -> device copy of the selected channel planes of a pinned NCHW batch in ONE call (set_input: fcgan_model.py:118-122 selects
+// the channels on the host and copies the result; here `rows` = batch samples, each contributing `width_bytes` contiguous bytes
+// -- the run of selected channel planes -- at `src_pitch` = bytes of a whole source sample).  Asynchronous when src is pinned.
+extern "C" int sgk_h2d_rows_async(void* dst, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t width_bytes, size_t rows,
+                                  void* stream) {
+  SGK_CHECK_ARG(dst && src_host && width_bytes > 0 && rows > 0 && dst_pitch >= width_bytes && src_pitch >= width_bytes,
+                "sgk_h2d_rows_async: bad argument");
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_pitch, src_host, src_pitch, width_bytes, rows, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy2DAsync");
+  return SGK_OK;
+}

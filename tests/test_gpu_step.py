@@ -231,3 +231,16 @@ def test_set_input_paths_agree(S):
             assert torch.equal(m.input.cpu(), want), (chan, src.device, src.is_pinned() if not src.is_cuda else None)
         m.set_input({"A": batch.clone().pin_memory(), "A_paths": ["x"]})
         assert m.h2d_bytes == (want.numel() if idx != [0, 2] else batch.numel()) * 4
+
+
+def test_set_input_pinned_strided_copy_selects_channels(S):
+    """set_input's fast path (pinned host batch, contiguous channel run): ONE strided H2D copy must equal the reference's
+    host-side index_select (fcgan_model.py:118-122), for a leading and a trailing channel run."""
+    from supervised_gan_b200.fcgan_model import FCGANModel
+    for which, idx in (("rg", [0, 1]), ("gb", [1, 2])):
+        m = FCGANModel(); m.initialize(make_opt(which_channel=which, fineSize=64, noiseSize=1, ngf=8, ndf=8, pool_size=0))
+        batch = (torch.rand(3, 3, 64, 64) * 2 - 1).pin_memory()
+        m.set_input({"A": batch, "A_paths": ["x"]})
+        torch.cuda.synchronize()
+        assert m.h2d_bytes == 3 * 2 * 64 * 64 * 4
+        assert torch.equal(m.input.cpu(), batch.index_select(1, torch.tensor(idx)))
