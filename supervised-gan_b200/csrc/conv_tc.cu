@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(IP_THREADS, 2)
 conv_window_persist_kernel(const __grid_constant__ ImPParams p, const __grid_constant__ ImPMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int S = p.stages;
   const uint32_t w_base = smem_base + (((uint32_t)S * p.stage_stride + 1023u) & ~1023u);   // weights: BN x 128 B, loaded once
   const uint32_t stg_base = w_base + (((uint32_t)p.BN * 128u + 1023u) & ~1023u);            // epilogue transpose: 128 x 128 B
@@ -934,43 +934,69 @@ conv_window_persist_kernel(const __grid_constant__ ImPParams p, const __grid_con
   uint32_t tmem_acc;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
 
+  // producer and MMA roles: warp-uniform loops, one elected lane issues, (slot, parity) ring counters, incrementally tracked
+  // tile coordinates and (high, low)-word descriptors (a lone warp pays ~5 clk per SASS instruction; the
+  // "1 us hand-offs" this kernel was tuned around in round 1 were its own issue loops)
+  const int ntiles = (int)p.total;
   if (warp == 0) {
     // =============================================================== TMA producer
-    if (lane == 0) {
+    const bool leader = elect_one_lane();
+    if (leader) {
       mbar_arrive_expect_tx(w_bar, (uint32_t)p.BN * 128u);
       tma_load_2d(w_base, &maps.w, 0, n0, w_bar);
-      const uint32_t patch_bytes = p.row_bytes * p.patch_rows;
-      int it = 0;
-      for (long long t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
-        const int s = it % S;
-        mbar_wait(empty_bar(s), (uint32_t)(((it / S) & 1) ^ 1));
-        const int n = (int)(t / per_img);
-        const int r2 = (int)(t - (long long)n * per_img);
-        const int ty0 = (r2 / p.tiles_x) * WN_TH, tx0 = (r2 % p.tiles_x) * WN_TW;
-        if (p.dbg & 4) { mbar_arrive(full_bar(s)); continue; }
-        mbar_arrive_expect_tx(full_bar(s), patch_bytes);
-        tma_load_3d(smem_base + (uint32_t)s * p.stage_stride, &maps.a, (tx0 * p.s + p.off) * p.Cg, ty0 * p.s + p.off, n, full_bar(s));
+    }
+    const uint32_t patch_bytes = p.row_bytes * p.patch_rows;
+    int s = 0;
+    uint32_t ph = 1;
+    int n = (int)blockIdx.x / per_img;
+    int r2 = (int)blockIdx.x - n * per_img;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      mbar_wait(empty_bar(s), ph);
+      if (leader) {
+        const int tyi = r2 / p.tiles_x;
+        const int ty0 = tyi * WN_TH, tx0 = (r2 - tyi * p.tiles_x) * WN_TW;
+        if (p.dbg & 4) {
+          mbar_arrive(full_bar(s));
+        } else {
+          mbar_arrive_expect_tx(full_bar(s), patch_bytes);
+          tma_load_3d(smem_base + (uint32_t)s * p.stage_stride, &maps.a, (tx0 * p.s + p.off) * p.Cg, ty0 * p.s + p.off, n, full_bar(s));
+        }
       }
+      r2 += (int)gridDim.x;
+      while (r2 >= per_img) { r2 -= per_img; ++n; }
+      if (++s == S) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // =============================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN);
-      mbar_wait(w_bar, 0);
-      int it = 0;
-      for (long long t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
-        const int s = it % S, acc = it % NA;
-        mbar_wait(tempty_bar(acc), (uint32_t)(((it / NA) & 1) ^ 1));   // the epilogue has drained this accumulator
-        mbar_wait(full_bar(s), (uint32_t)((it / S) & 1));
-        tc_fence_after();
-        const uint32_t a_addr = smem_base + (uint32_t)s * p.stage_stride;
+    const bool leader = elect_one_lane();
+    const uint32_t idesc = make_idesc_tf32(TC_BM, p.BN);
+    // A: no-swizzle K-major windows of the raw patch (LBO 16 B = the same window one pixel further, SBO = s image rows);
+    // B: K-major SWIZZLE_128B weights.  high words are constant, low words are 16-byte units.
+    const uint32_t a_hi = ((((uint32_t)p.s * p.row_bytes) >> 4) & 0x3FFFu) | (1u << 14);
+    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = (smem_base >> 4) | (1u << 16), b_lo = (w_base >> 4) | (1u << 16);
+    const uint32_t stage_units = p.stage_stride >> 4, row_units = p.row_bytes >> 4;
+    const int nk = (p.dbg & 2) ? 1 : 4;
+    mbar_wait(w_bar, 0);
+    int s = 0, acc = 0;
+    uint32_t ph = 0, aph = 1, a_lo = a_lo0, dcol = tmem_acc;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      mbar_wait(tempty_bar(acc), aph);                  // the epilogue has drained this accumulator
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < ((p.dbg & 2) ? 1 : 4); ++kk)   // tap row kk: windows of the raw patch
-          umma_tf32(tmem_acc + (uint32_t)(acc * p.BN), make_noswz_kmajor_desc(a_addr + kk * p.row_bytes, 16u, (uint32_t)p.s * p.row_bytes),
-                    make_sw128_kmajor_desc(w_base + kk * 32), idesc, (uint32_t)(kk != 0));
+        for (int kk = 0; kk < 4; ++kk)                     // tap row kk: windows of the raw patch
+          if (kk < nk)
+            umma_tf32(dcol, ((uint64_t)a_hi << 32) | (a_lo + row_units * kk), ((uint64_t)b_hi << 32) | (b_lo + 2u * kk), idesc,
+                      (uint32_t)(kk != 0));
         umma_commit(empty_bar(s));
         umma_commit(tfull_bar(acc));
       }
+      a_lo += stage_units;
+      if (++s == S) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+      dcol += (uint32_t)p.BN;
+      if (++acc == NA) { acc = 0; aph ^= 1u; dcol = tmem_acc; }
     }
   } else if (warp >= 4) {
     // =============================================================== epilogue (warp w owns TMEM lanes 32*(w-4)...)
@@ -993,10 +1019,13 @@ conv_window_persist_kernel(const __grid_constant__ ImPParams p, const __grid_con
     long long t = blockIdx.x;
     int n = (int)(t / per_img);
     int r2 = (int)(t - (long long)n * per_img);
+    int acc = -1;
+    uint32_t eph = 1;
     for (; t < p.total; t += gridDim.x, ++it) {
-      const int acc = it % NA;
-      const int ty0 = (r2 / p.tiles_x) * WN_TH, tx0 = (r2 % p.tiles_x) * WN_TW;
-      mbar_wait(tfull_bar(acc), (uint32_t)((it / NA) & 1));
+      if (++acc == NA || it == 0) { acc = 0; eph ^= 1u; }
+      const int tyi = r2 / p.tiles_x;
+      const int ty0 = tyi * WN_TH, tx0 = (r2 - tyi * p.tiles_x) * WN_TW;
+      mbar_wait(tfull_bar(acc), eph);
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < p.BN; cc += 32) {
