@@ -106,13 +106,54 @@ def line_config(args, world):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock / power / throttle reasons sampled DURING a timed region.  NVML (nvidia_ml_py) is polled every 2 ms from a
+    thread -- the timed region of the default run is only ~80 ms, shorter than `nvidia-smi -lms` needs to start -- with the
+    nvidia-smi loop as the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
     def __init__(self, gpu):
         self.gpu, self.proc, self.lines = gpu, None, []
+        self.nvml, self.handle, self.thread, self.stop_flag, self.samples = None, None, None, False, []
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        return pynvml, h
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while True:
+            try:
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(mask)))
+            except Exception:
+                pass
+            if self.stop_flag:
+                return
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.smax = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.stop_flag, self.samples = False, []
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -126,6 +167,17 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(float(x[0]) for x in self.samples)
+            reasons = set()
+            for _, _, mask in self.samples:
+                for bit, name in self.BITS.items():
+                    if mask & bit:
+                        reasons.add(name)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(reasons),
+                    "samples": len(sm), "power_w_max": max((x[1] for x in self.samples), default=None), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -144,7 +196,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+                "samples": len(sm), "power_w_max": max(power) if power else None, "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------ reference legs
@@ -428,9 +480,10 @@ def run_ours(args):
     gpu_launches = launches_per_step * args.steps if used_graph else eager_launches
 
     # ---------------- timed region 2: end to end through the public API, H2D + D2H inside
-    for i in range(3):
+    for i in range(max(10, args.warmup)):     # untimed: the same three calls as the timed loop (copy stream, loss read-back path)
         m.set_input({"A": host_batches[i % 2], "A_paths": ["synthetic"]})
         m.optimize_parameters()
+        m.get_current_errors()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = args.steps
