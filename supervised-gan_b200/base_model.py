@@ -100,6 +100,36 @@ class BaseModel(object):
                 for p in self.params:
                     p.requires_grad_(True)
 
+    # ------------------------------------------------------------------ host <-> device edges of a step
+    def _h2d_channels(self, src, idx, dst):
+        """dst <- src.index_select(1, idx) for a host batch (set_input of cgan_model.py:62-78 / twostage_cycle_model.py:98-114).
+        A pinned fp32 batch whose selected channels are a contiguous run crosses PCIe as ONE asynchronous strided copy of just
+        those planes; anything else takes the reference's route (host-side select, then copy).  Returns the bytes copied."""
+        idx_l = [int(i) for i in (idx.tolist() if torch.is_tensor(idx) else idx)]
+        shape = (src.shape[0], len(idx_l)) + tuple(src.shape[2:])
+        if dst is None or tuple(dst.shape) != shape:
+            if getattr(self, "_graph", None) is not None:
+                raise RuntimeError("cuda_graph: the batch shape is frozen after capture (got %s)" % (shape,))
+            dst = torch.empty(shape, device=self.device)
+        if (not src.is_cuda and src.is_pinned() and src.is_contiguous() and src.dtype == torch.float32 and src.dim() == 4
+                and idx_l == list(range(idx_l[0], idx_l[0] + len(idx_l)))):
+            plane = src.shape[2] * src.shape[3] * 4
+            _lib.check(_lib.load().sgk_h2d_rows_async(dst.data_ptr(), len(idx_l) * plane, src.data_ptr() + idx_l[0] * plane,
+                                                      src.shape[1] * plane, len(idx_l) * plane, src.shape[0],
+                                                      torch.cuda.current_stream().cuda_stream), "h2d_rows_async")
+            return dst, dst.numel() * 4
+        sel = src.index_select(1, torch.as_tensor(idx_l, dtype=torch.long, device=src.device))
+        dst.copy_(sel, non_blocking=True)
+        return dst, (0 if src.is_cuda else dst.numel() * 4)
+
+    def _read_scalars(self, named):
+        """OrderedDict of Python floats from (name, 0-d tensor or number) pairs with ONE device-to-host copy."""
+        names = [k for k, _ in named]
+        dev = [v.detach().reshape(()).float() if torch.is_tensor(v) else torch.tensor(float(v), device=self.device) for _, v in named]
+        vals = torch.stack(dev).tolist()
+        from collections import OrderedDict
+        return OrderedDict(zip(names, vals))
+
     # ------------------------------------------------------------------ parallel discriminator scales
     def _for_each_net(self, nets, fn):
         """[fn(net) for net in nets] with every net but the first on its own CUDA stream, forked from and joined to the current

@@ -62,19 +62,14 @@ class CGANModel(BaseModel):
     def set_input(self, input):
         AtoB = self.opt.which_direction == 'AtoB'
         if self.opt.dataset_mode == 'aligned':
-            input_A = input['A' if AtoB else 'B'].index_select(1, self.chnl_idx_input[0])
-            input_B = input['B' if AtoB else 'A'].index_select(1, self.chnl_idx_input[1])
+            src_A, src_B = input['A' if AtoB else 'B'], input['B' if AtoB else 'A']
         elif self.opt.dataset_mode == 'single':
-            input_A = input['A'].index_select(1, self.chnl_idx_input[0])
-            input_B = input['A'].index_select(1, self.chnl_idx_input[1])
+            src_A = src_B = input['A']
         else:
             raise NotImplementedError('Dataset mode [%s] is not recognized' % self.opt.dataset_mode)
-        if self.input_A.shape != input_A.shape:
-            self.input_A = torch.empty(input_A.shape, device=self.device)
-        if self.input_B.shape != input_B.shape:
-            self.input_B = torch.empty(input_B.shape, device=self.device)
-        self.input_A.copy_(input_A, non_blocking=True)
-        self.input_B.copy_(input_B, non_blocking=True)
+        self.input_A, na = self._h2d_channels(src_A, self.chnl_idx_input[0], self.input_A)
+        self.input_B, nb = self._h2d_channels(src_B, self.chnl_idx_input[1], self.input_B)
+        self.h2d_bytes = na + nb
         self.image_paths = input['A_paths' if AtoB else 'B_paths']
 
     def _draw_noise(self):
@@ -144,8 +139,8 @@ class CGANModel(BaseModel):
                 self.sample_noise()
 
     def get_current_errors(self):
-        return OrderedDict([('G_GAN', float(self.loss_G)), ('G_L1', float(self.loss_G_L1)),
-                            ('D_real', float(self.loss_D_real)), ('D_fake', float(self.loss_D_fake))])
+        return self._read_scalars([('G_GAN', self.loss_G), ('G_L1', self.loss_G_L1), ('D_real', self.loss_D_real),
+                                   ('D_fake', self.loss_D_fake)])
 
     def get_current_visuals(self, save_as_single_image=False):
         out = OrderedDict([('real_A', self.real_A.detach()), ('fake_B', self.fake_B.detach())])

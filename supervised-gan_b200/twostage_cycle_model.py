@@ -98,19 +98,14 @@ class TwoStageCycleModel(BaseModel):
     def set_input(self, input):
         AtoB = self.opt.which_direction == 'AtoB'
         if self.opt.dataset_mode == 'aligned':
-            input_A = input['A' if AtoB else 'B'].index_select(1, self.chnl_idx_input[0])
-            input_B = input['B' if AtoB else 'A'].index_select(1, self.chnl_idx_input[1])
+            src_A, src_B = input['A' if AtoB else 'B'], input['B' if AtoB else 'A']
         elif self.opt.dataset_mode == 'single':
-            input_A = input['A'].index_select(1, self.chnl_idx_input[0])
-            input_B = input['A'].index_select(1, self.chnl_idx_input[1])
+            src_A = src_B = input['A']
         else:
             raise NotImplementedError('Dataset mode [%s] is not recognized' % self.opt.dataset_mode)
-        if self.input_A.shape != input_A.shape:
-            self.input_A = torch.empty(input_A.shape, device=self.device)
-        if self.input_B.shape != input_B.shape:
-            self.input_B = torch.empty(input_B.shape, device=self.device)
-        self.input_A.copy_(input_A, non_blocking=True)
-        self.input_B.copy_(input_B, non_blocking=True)
+        self.input_A, na = self._h2d_channels(src_A, self.chnl_idx_input[0], self.input_A)
+        self.input_B, nb = self._h2d_channels(src_B, self.chnl_idx_input[1], self.input_B)
+        self.h2d_bytes = na + nb
         self.image_paths = input['A_paths' if AtoB else 'B_paths']
 
     def _draw_noises(self):
@@ -240,12 +235,10 @@ class TwoStageCycleModel(BaseModel):
                 self.sample_noise()
 
     def get_current_errors(self):
-        f = float
-        return OrderedDict([('G1_GAN', f(self.loss_G1_GAN)), ('G2_GAN', f(self.loss_G2_GAN)), ('G2_L1', f(self.loss_G2_L1)),
-                            ('F2_CE', f(self.loss_F2_CE)), ('G2_real_cycle', f(self.loss_G2_real_cycle)),
-                            ('G2_fake_cycle', f(self.loss_G2_fake_cycle)), ('D1_real', f(self.loss_D1_real)),
-                            ('D1_fake', f(self.loss_D1_fake)), ('D2_real', f(self.loss_D2_real)),
-                            ('D2_fake', f(self.loss_D2_fake))])
+        return self._read_scalars([('G1_GAN', self.loss_G1_GAN), ('G2_GAN', self.loss_G2_GAN), ('G2_L1', self.loss_G2_L1),
+                                   ('F2_CE', self.loss_F2_CE), ('G2_real_cycle', self.loss_G2_real_cycle),
+                                   ('G2_fake_cycle', self.loss_G2_fake_cycle), ('D1_real', self.loss_D1_real),
+                                   ('D1_fake', self.loss_D1_fake), ('D2_real', self.loss_D2_real), ('D2_fake', self.loss_D2_fake)])
 
     def get_current_visuals(self, save_as_single_image=False):
         return OrderedDict([('real_A', self.real_A.detach()), ('fake_B_from_real_A', self.fake_B_from_real_A.detach()),
