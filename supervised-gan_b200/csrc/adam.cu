@@ -28,9 +28,12 @@ constexpr int ADAM_MAX_BLOCKS = 320;
 // has to be staged through device memory and a captured CUDA graph carries it
 struct AdamLaunch {
   SgkAdamTensor t[ADAM_MAX_TENSORS];
-  int32_t block_chunk[ADAM_MAX_BLOCKS];
+  int32_t block_chunk[ADAM_MAX_BLOCKS];    // first 4096-element chunk of the block
   uint8_t block_tensor[ADAM_MAX_BLOCKS];
+  uint8_t block_count[ADAM_MAX_BLOCKS];    // consecutive chunks the block walks (1 for small optimisers; up to ADAM_MAX_CPB for the
+                                           // 50 M-parameter U-Nets, which used to take 41 launches of 320 one-chunk blocks)
 };
+constexpr int ADAM_MAX_CPB = 64;
 
 __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const __grid_constant__ AdamLaunch L,
                                                             const int64_t* __restrict__ step_dev,
@@ -48,8 +51,34 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const __grid_constan
   const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const float w1 = 1.f - b1, omb2 = 1.f - b2;
   const SgkAdamTensor T = L.t[L.block_tensor[blockIdx.x]];
-  const int64_t base = (int64_t)L.block_chunk[blockIdx.x] * ADAM_BLOCK_ELEMS;
   const bool aligned = ((((uintptr_t)T.p) | ((uintptr_t)T.g) | ((uintptr_t)T.m) | ((uintptr_t)T.v)) & 15) == 0;
+  const int nchunks = L.block_count[blockIdx.x];
+  for (int ck = 0; ck < nchunks; ++ck) {
+  const int64_t base = (int64_t)(L.block_chunk[blockIdx.x] + ck) * ADAM_BLOCK_ELEMS;
+  if (aligned && base + ADAM_BLOCK_ELEMS <= T.n) {
+    // full chunk: all 16 loads of the thread are issued before the first dependent instruction (memory-level parallelism)
+    float4 p[ADAM_VEC_PER_THREAD], g[ADAM_VEC_PER_THREAD], m[ADAM_VEC_PER_THREAD], v[ADAM_VEC_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < ADAM_VEC_PER_THREAD; ++u) {
+      const int64_t i = base + ((int64_t)u * ADAM_THREADS + threadIdx.x) * 4;
+      p[u] = *reinterpret_cast<const float4*>(T.p + i);
+      g[u] = *reinterpret_cast<const float4*>(T.g + i);
+      m[u] = *reinterpret_cast<const float4*>(T.m + i);
+      v[u] = *reinterpret_cast<const float4*>(T.v + i);
+    }
+#pragma unroll
+    for (int u = 0; u < ADAM_VEC_PER_THREAD; ++u) {
+      const int64_t i = base + ((int64_t)u * ADAM_THREADS + threadIdx.x) * 4;
+      adam_elem(p[u].x, g[u].x * gs, m[u].x, v[u].x, w1, b1, b2, omb2, step_size, bc2_sqrt, eps);
+      adam_elem(p[u].y, g[u].y * gs, m[u].y, v[u].y, w1, b1, b2, omb2, step_size, bc2_sqrt, eps);
+      adam_elem(p[u].z, g[u].z * gs, m[u].z, v[u].z, w1, b1, b2, omb2, step_size, bc2_sqrt, eps);
+      adam_elem(p[u].w, g[u].w * gs, m[u].w, v[u].w, w1, b1, b2, omb2, step_size, bc2_sqrt, eps);
+      *reinterpret_cast<float4*>(T.p + i) = p[u];
+      *reinterpret_cast<float4*>(T.m + i) = m[u];
+      *reinterpret_cast<float4*>(T.v + i) = v[u];
+    }
+    continue;
+  }
 #pragma unroll
   for (int u = 0; u < ADAM_VEC_PER_THREAD; ++u) {
     int64_t i = base + ((int64_t)u * ADAM_THREADS + threadIdx.x) * 4;
@@ -73,6 +102,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const __grid_constan
         T.p[j] = p; T.m[j] = m; T.v[j] = v;
       }
     }
+  }
   }
 }
 
@@ -98,6 +128,12 @@ extern "C" int sgk_adam_multi_tensor(const SgkAdamTensor* tensors_host, int n_te
     nt = 0; nb = 0;
     return SGK_OK;
   };
+  // chunks per block: 1 while everything fits one launch of ADAM_MAX_BLOCKS blocks, more for large optimisers
+  int64_t total_chunks = 0;
+  for (int i = 0; i < n_tensors; ++i) total_chunks += (tensors_host[i].n + ADAM_BLOCK_ELEMS - 1) / ADAM_BLOCK_ELEMS;
+  int64_t cpb = (total_chunks + ADAM_MAX_BLOCKS - 1) / ADAM_MAX_BLOCKS;
+  if (cpb < 1) cpb = 1;
+  if (cpb > ADAM_MAX_CPB) cpb = ADAM_MAX_CPB;
   for (int i = 0; i < n_tensors; ++i) {
     const SgkAdamTensor& T = tensors_host[i];
     SGK_CHECK_ARG(T.p && T.g && T.m && T.v && T.n >= 0, "sgk_adam_multi_tensor: tensor %d has a null pointer", i);
@@ -107,9 +143,11 @@ extern "C" int sgk_adam_multi_tensor(const SgkAdamTensor* tensors_host, int n_te
       if (nt == ADAM_MAX_TENSORS || nb == ADAM_MAX_BLOCKS) { int rc = flush(); if (rc) return rc; }
       L.t[nt] = T;
       while (c < chunks && nb < ADAM_MAX_BLOCKS) {
+        const int64_t take = chunks - c < cpb ? chunks - c : cpb;
         L.block_tensor[nb] = (uint8_t)nt;
         L.block_chunk[nb] = (int32_t)c;
-        ++nb; ++c;
+        L.block_count[nb] = (uint8_t)take;
+        ++nb; c += take;
       }
       ++nt;
     }
