@@ -1189,7 +1189,12 @@ static int conv_fwd_tc_tile(const SgkConvDesc* d, const GatherPlan& g, const flo
   // once through shared memory instead of once per tap and phase)
   static const bool thin_out_tma = getenv("SGK_TC_THIN_TMA") != nullptr && atoi(getenv("SGK_TC_THIN_TMA")) != 0;
   const bool thin_out = thin_out_tma && (g.Cg % 32) == 0 && g.Co <= 16;   // image-producing / image-gradient layers
-  if (!im2col && !window_shape && !thin_out && !tc_thin && ((g.Cg % 32) != 0 || (g.Co % 32) != 0)) return SGK_EUNSUPPORTED;
+  // direct conv from a 3..31-channel image into >= 32 channels (the conditional discriminator's first layer: 3 -> 64 on 512^2):
+  // the cp.async-gather tensor-core tile with flattened (tap, channel) K slots measured 27 us against 66 us for the CUDA-core
+  // edge kernel (cgan step, profiles/r2_layer_table_cgan.md); its input gradient stays on CUDA cores (76 vs 48 us)
+  static const bool thin_in_on = !(getenv("SGK_TC_THIN_IN") != nullptr && atoi(getenv("SGK_TC_THIN_IN")) == 0);
+  const bool thin_in = thin_in_on && g.transposed_type == 0 && g.nphase == 1 && g.Cg >= 3 && g.Cg < 32 && (g.Co % 32) == 0;
+  if (!im2col && !window_shape && !thin_out && !tc_thin && !thin_in && ((g.Cg % 32) != 0 || (g.Co % 32) != 0)) return SGK_EUNSUPPORTED;
   // N tile: a divisor of Cout in {256,128,64,32}, or one 16-wide tile for thin outputs (Cout <= 16: images, logits)
   int BN = pick_bn(g.Co);
   if (BN == 0) {
