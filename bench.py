@@ -106,15 +106,16 @@ def line_config(args, world):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled DURING a timed region.  NVML (nvidia_ml_py) is polled every 2 ms from a
-    thread -- the timed region of the default run is only ~80 ms, shorter than `nvidia-smi -lms` needs to start -- with the
+    """SM clock / power / throttle reasons sampled DURING a timed region.  NVML (nvidia_ml_py) is polled every 5 ms from a
+    thread, on rank 0 only -- the timed region of the default run is only ~80 ms, shorter than `nvidia-smi -lms` needs to start -- with the
     nvidia-smi loop as the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
-    def __init__(self, gpu):
+    def __init__(self, gpu, enabled=True, period=0.005):
         self.gpu, self.proc, self.lines = gpu, None, []
+        self.enabled, self.period = enabled, period        # one sampling rank per job: 8 polling threads on 16 host cores cost steps
         self.nvml, self.handle, self.thread, self.stop_flag, self.samples = None, None, None, False, []
 
     def _nvml_handle(self):
@@ -142,9 +143,11 @@ class ClockSampler:
                 pass
             if self.stop_flag:
                 return
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             self.nvml, self.handle = self._nvml_handle()
             self.smax = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
@@ -167,6 +170,8 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if not self.enabled:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "not sampled on this rank"}
         if self.nvml is not None:
             self.stop_flag = True
             self.thread.join(timeout=1.0)
@@ -460,7 +465,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         m.optimize_parameters()
     # ---------------- timed region 1: device-resident inputs
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, enabled=(rank == 0))
     barrier()
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -508,7 +513,7 @@ def run_ours(args):
     sustained = None
     if args.sustain > 0:
         n_s = max(args.steps, int(args.sustain / max(ms / args.steps * 1e-3, 1e-6)))
-        clocks2 = ClockSampler(local)
+        clocks2 = ClockSampler(local, enabled=(rank == 0))
         barrier()
         clocks2.start()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
