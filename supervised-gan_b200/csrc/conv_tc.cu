@@ -1092,7 +1092,7 @@ static int conv_fwd_tc_tile(const SgkConvDesc* d, const GatherPlan& g, const flo
 
 // Kernel choice per problem shape.  conv_patch_tc_kernel (one input patch per tile, persistent) and conv_tma_tc_kernel (one
 // activation tile per tap, 3 CTAs per SM) win on different layers -- wave quantisation of the persistent tiles, N width and
-// stride all matter (profiles/r2_patch_layers.md) -- so the first eager call of a shape times both on the caller's stream
+// stride all matter (profiles/r2_layer_table_*.md) -- so the first eager call of a shape times both on the caller's stream
 // (CUDA events, best of 3) and the winner is cached for the process.  While a CUDA graph is being captured nothing can be
 // timed: an unseen shape then takes the static rule (strided / sub-pixel problems with <= 64 output channels -> patch).
 // SGK_PATCH: 0 = never patch, 1 = tuned (default), 2 = patch whenever eligible, 3 = static rule only.

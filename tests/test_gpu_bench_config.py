@@ -19,6 +19,8 @@ Observed values are appended to gpurun_out/parity_metrics.jsonl (diagnostics onl
 import argparse
 import json
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -275,6 +277,21 @@ def test_conv_tf32_appendix_b_shapes(S, case):
     if Ci % 32 == 0 and Co % 32 == 0:
         assert "conv_tma_tc_kernel" in kern or "conv_patch_tc_kernel" in kern, kern   # the tensor-core kernel ran
     assert e["fwd"] <= 2e-3 and e["dgrad"] <= 2e-3 and e["wgrad"] <= 2e-3 and e["bgrad"] <= 1e-4, e
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_conv_tf32_parity_with_forced_kernel_choice(mode):
+    """The forward / dgrad kernel of a shape is picked by timing, so one run checks only the winner.  SGK_PATCH
+    is read once per process: a child process repeats the per-conv parity tests (the Appendix-B shapes above and
+    tests/test_gpu_tf32.py::test_conv_tf32) with the choice forced to the tile kernel (0) and to the patch kernel wherever
+    it is eligible (2), so both candidates are held to the same 2e-3 bound on every shape."""
+    env = dict(os.environ, SGK_PATCH=mode)
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_bench_config.py"),
+           os.path.join(ROOT, "tests", "test_gpu_tf32.py"), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+           "-k", "(test_conv_tf32_appendix_b_shapes or test_conv_tf32) and not forced"]
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, "SGK_PATCH=%s\n%s\n%s" % (mode, r.stdout[-4000:], r.stderr[-2000:])
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
 
 
 # ------------------------------------------------------------------------------------------------ (c)
