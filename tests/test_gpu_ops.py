@@ -459,3 +459,18 @@ def test_l1_weight_map_kernel(S):
     arr = (ctypes.c_float * 2)(2.0, 4.0)
     L.check(L.load().sgk_l1_weight_map(ta.data_ptr(), w.data_ptr(), 2, 3, 33 * 17, arr, 2, torch.cuda.current_stream().cuda_stream), "wm")
     close(w.cpu().numpy(), O.l1_weight_map(a, [2.0, 4.0]), 2e-6, "l1 weight map")
+
+
+def test_instance_norm_three_kernel_path_forced():
+    """InstanceNorm planes normally take the cooperative fused passes; the statistics / finalize / apply kernels remain the
+    path for planes the cooperative grid cannot hold (and for BatchNorm).  SGK_NORM_FUSED is read once per process, so a child
+    process repeats the InstanceNorm op test and the golden fcgan steps with the fused passes switched off."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ops.py"), os.path.join(root, "tests", "test_gpu_step.py"),
+           "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k", "test_instance_norm_act or test_fcgan_step_golden"]
+    r = subprocess.run(cmd, env=dict(os.environ, SGK_NORM_FUSED="0"), cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, "%s\n%s" % (r.stdout[-4000:], r.stderr[-2000:])
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
