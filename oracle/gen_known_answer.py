@@ -70,12 +70,85 @@ def run_reference():
     return blob
 
 
+def run_reference_cgan():
+    """BASELINE configs[1]: unet_256 G (ngf 64) + n_layers D x2 (ndf 64, n_layers 3 / 4, scale 1 / 1) on cat(A, B), BCE,
+    lambda_A 10, class-weighted L1 (weights 2 4), batch 1, 512x512.  Recipe: seed(1) -> CGANModel.initialize (define_G, then
+    the define_D's, cgan_model.py:60-80; no draw before them) -> BOTH image batches drawn up front from the global generator
+    (the noise draws of forward(), cgan_model.py:135, which the U-Net ignores, then cannot shift them) -> two steps."""
+    Model = R.load_model_class("cgan")
+    seed(1)
+    opt = R.cgan_opt(which_model_netG="unet_256", ngf=64, ndf=64, scale_factor=[1, 1], n_layers_D=[3, 4],
+                     lambda_D=[0.5, 0.5], weights=[2.0, 4.0], pool_size=0, noiseSize=4)
+    m = Model()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.initialize(opt)
+    blob = {"init.G": state_digest(m.netG)}
+    for i, d in enumerate(m.netD):
+        blob["init.D%d" % i] = state_digest(d)
+    xs = [torch.rand(1, 3, 512, 512) * 2 - 1 for _ in range(STEPS)]
+    for t in range(STEPS):
+        m.set_input({"A": xs[t], "A_paths": ["x"]})
+        m.optimize_parameters()
+        blob["real_A%d.digest" % t] = digest(m.real_A)
+        blob["real_B%d.digest" % t] = digest(m.real_B)
+        blob["fake_B%d.digest" % t] = digest(m.fake_B)
+        blob["loss%d" % t] = np.array([float(v.detach()) for v in (m.loss_G, m.loss_G_L1, m.loss_D_real, m.loss_D_fake)])
+    blob["meta.steps"] = np.array(STEPS)
+    return blob
+
+
+def run_reference_twostage():
+    """BASELINE configs[2] (README.md:18 recipe): fcgan G1 (ngf1 32, noise 8x4x4) -> bilinear x2 -> CRN G2 (ngf2 64, bilinear,
+    2 layers per block, noise 8x8x8), unet_128 F2 (nff2 32), D1 x2 (scales 1 / 2), D2 x4 (n_layers 3 / 4, scales 1 / 1 / 2 / 2),
+    batch 1, 512x512.  Recipe: seed(2) -> TwoStageCycleModel.initialize (G1, G2, F2, D1's, D2's, twostage_cycle_model.py:46-100)
+    -> both image batches up front -> two steps; the noise pair the reference draws per step is stored (640 floats)."""
+    Model = R.load_model_class("twostage_cycle")
+    seed(2)
+    m = Model()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.initialize(R.twostage_opt(pool_size=0))
+    blob = {}
+    for lab, net in (("G1", m.netG1), ("G2", m.netG2), ("F2", m.netF2)):
+        blob["init." + lab] = state_digest(net)
+    for i, d in enumerate(m.netD1):
+        blob["init.D1_%d" % i] = state_digest(d)
+    for i, d in enumerate(m.netD2):
+        blob["init.D2_%d" % i] = state_digest(d)
+    xs = [torch.rand(1, 3, 512, 512) * 2 - 1 for _ in range(STEPS)]
+    for t in range(STEPS):
+        m.set_input({"A": xs[t], "A_paths": ["x"]})
+        m.optimize_parameters()
+        blob["real_A%d.digest" % t] = digest(m.real_A)
+        blob["real_B%d.digest" % t] = digest(m.real_B)
+        blob["noise1_%d" % t] = m.noise1.detach().numpy().copy()
+        blob["noise2_%d" % t] = m.noise2.detach().numpy().copy()
+        for name in ("fake_A", "fake_B_from_fake_A", "recon_fake_A"):
+            blob["%s%d.digest" % (name, t)] = digest(getattr(m, name))
+        blob["loss%d" % t] = np.array([float(v.detach()) for v in (
+            m.loss_G, m.loss_G1_GAN, m.loss_G2_GAN, m.loss_G2_L1, m.loss_F2_CE, m.loss_G2_real_cycle, m.loss_G2_fake_cycle,
+            m.loss_D1_real, m.loss_D1_fake, m.loss_D2_real, m.loss_D2_fake)])
+    blob["meta.steps"] = np.array(STEPS)
+    return blob
+
+
+RUNS = {"fcgan_config1": run_reference, "cgan_config2": run_reference_cgan, "twostage_config3": run_reference_twostage}
+
+
+def path_of(name):
+    return os.path.join(os.path.dirname(OUT), name + "_known_answer.npz")
+
+
 def main():
     if not R.available():
         raise SystemExit("reference tree not present")
-    blob = run_reference()
-    np.savez_compressed(OUT, **blob)
-    print("wrote", OUT, os.path.getsize(OUT), "bytes; step-0 losses", blob["loss0"])
+    import time
+    for name, fn in RUNS.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
+        t0 = time.time()
+        blob = fn()
+        np.savez_compressed(path_of(name), **blob)
+        print("wrote", path_of(name), os.path.getsize(path_of(name)), "bytes in %.1f s; step-0 losses" % (time.time() - t0), blob["loss0"])
 
 
 if __name__ == "__main__":

@@ -134,3 +134,220 @@ def test_cuda_step_reproduces_known_answer(ka, replay, precision, loss_tol, img_
                 assert abs(d[1] - ka["fake0.digest"][1]) <= img_tol * m.fake.numel()
     finally:
         S.set_precision("fp32")
+
+
+# ================================================================================================ configs 2 and 3
+# The same construction for BASELINE configs[1] (cgan) and configs[2] (two-stage DSGAN recipe) at FULL size: the unmodified
+# reference model classes produced the fixtures (oracle/gen_known_answer.run_reference_cgan / _twostage); the replays below
+# re-draw weights and images from the seed with our factories, called exactly as the reference's initialize() calls its own
+# (cgan_model.py:59-80, twostage_cycle_model.py:46-96).
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _log(name, d):
+    import json
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "parity_metrics.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **d}) + "\n")
+    except OSError:
+        pass
+
+
+def _sd(n):
+    return {k: v.detach().clone() for k, v in n.state_dict().items()}
+
+
+def _split_rg_b(x):
+    return x[:, :2].contiguous(), x[:, 2:3].contiguous()       # which_channel 'rg_b': A = (r, g), B = (b)
+
+
+def _replay_cgan():
+    import supervised_gan_b200 as S
+    nw = S.networks
+    K.seed(1)
+    G = nw.define_G(2, 1, 64, "unet_256", "instance", False, n_layers_G=5, use_residual=False, use_fcn=True, noise_nc=8,
+                    add_gaussian_noise=False, gaussian_sigma=0.1, upsample_mode="convt", n_layers_CRN_block=1,
+                    share_label_weights=True, n_layers_G_skip=-1, gpu_ids=[])
+    Ds = [nw.define_D(3, 64, "n_layers", n_layers_D=n, norm="instance", use_sigmoid=True, scale_factor=1, gpu_ids=[])
+          for n in (3, 4)]
+    init = {"G": K.state_digest(G), **{"D%d" % i: K.state_digest(d) for i, d in enumerate(Ds)}}
+    reals = [_split_rg_b(torch.rand(1, 3, 512, 512) * 2 - 1) for _ in range(K.STEPS)]
+    return {"sdG": _sd(G), "sdDs": [_sd(d) for d in Ds], "init": init, "reals": reals}
+
+
+def _replay_twostage():
+    import supervised_gan_b200 as S
+    nw = S.networks
+    K.seed(2)
+    G1 = nw.define_G(2, 0, 32, "fcgan", "instance", False, n_layers_G=5, use_residual=False, use_fcn=True, noise_nc=8,
+                     add_gaussian_noise=False, gaussian_sigma=0.1, upsample_mode="convt", n_layers_CRN_block=1,
+                     share_label_weights=True, gpu_ids=[])
+    G2 = nw.define_G(2, 1, 64, "crn", "instance", False, n_layers_G=5, use_residual=False, use_fcn=False, noise_nc=8,
+                     add_gaussian_noise=False, gaussian_sigma=0.1, upsample_mode="bilinear", n_layers_CRN_block=2,
+                     share_label_weights=True, gpu_ids=[])
+    F2 = nw.define_G(1, 2, 32, "unet_128", "instance", False, n_layers_G=5, use_residual=False, use_fcn=False, noise_nc=8,
+                     add_gaussian_noise=False, gaussian_sigma=0.1, upsample_mode="bilinear", n_layers_CRN_block=2,
+                     share_label_weights=True, gpu_ids=[])
+    D1 = [nw.define_D(2, 32, "n_layers", n_layers_D=3, norm="instance", use_sigmoid=True, scale_factor=s, num_classes=2, gpu_ids=[])
+          for s in (1, 2)]
+    D2 = [nw.define_D(3, 64, "n_layers", n_layers_D=n, norm="instance", use_sigmoid=True, scale_factor=s, num_classes=2, gpu_ids=[])
+          for s, n in zip((1, 1, 2, 2), (3, 4, 3, 4))]
+    init = {"G1": K.state_digest(G1), "G2": K.state_digest(G2), "F2": K.state_digest(F2),
+            **{"D1_%d" % i: K.state_digest(d) for i, d in enumerate(D1)}, **{"D2_%d" % i: K.state_digest(d) for i, d in enumerate(D2)}}
+    reals = [_split_rg_b(torch.rand(1, 3, 512, 512) * 2 - 1) for _ in range(K.STEPS)]
+    return {"G1": _sd(G1), "G2": _sd(G2), "F2": _sd(F2), "D1": [_sd(d) for d in D1], "D2": [_sd(d) for d in D2],
+            "init": init, "reals": reals}
+
+
+@pytest.fixture(scope="module")
+def replay_cgan():
+    return _replay_cgan()
+
+
+@pytest.fixture(scope="module")
+def replay_twostage():
+    return _replay_twostage()
+
+
+def _check_seeded(kb, rp):
+    for name, dig in rp["init"].items():
+        np.testing.assert_array_equal(dig, kb["init." + name], err_msg="initial weights of net" + name)
+    for t in range(K.STEPS):
+        np.testing.assert_array_equal(K.digest(rp["reals"][t][0]), kb["real_A%d.digest" % t])
+        np.testing.assert_array_equal(K.digest(rp["reals"][t][1]), kb["real_B%d.digest" % t])
+
+
+TWOSTAGE_CFG = dict(n_layers_G1=5, use_fcn1=True, crn_mode="bilinear", crn_blocks=2, f2_downs=7, n_layers_D1=[3, 3],
+                    scale_factor1=[1, 2], lambda_D1=[0.5, 0.4], n_layers_D2=[3, 4, 3, 4], scale_factor2=[1, 1, 2, 2],
+                    lambda_D2=[0.3, 0.3, 0.2, 0.2], GAN_losses_D2=["real_fake"], GAN_losses_G2=["real_fake"], lambda_A=10.0,
+                    lambda_B=10.0, lambda_A_cycle=5.0, lambda_fake_cycle=1.0, lr1=2e-4, lr2=2e-4, beta1=0.5, sc=2, weights=None)
+
+
+def test_cgan_config2_oracle_port_reproduces_reference(replay_cgan):
+    kb, rp = np.load(K.path_of("cgan_config2")), replay_cgan
+    _check_seeded(kb, rp)
+    o = ON.CganStep(rp["sdG"], rp["sdDs"], num_downs=8, n_layers_D=(3, 4), scale_factor=(1, 1), lambda_D=(0.5, 0.5),
+                    lambda_A=10.0, weights=[2.0, 4.0], dtype=torch.float32)
+    got = o.step(*rp["reals"][0])
+    np.testing.assert_allclose(np.asarray(got, dtype=np.float64), kb["loss0"], rtol=5e-6)
+    np.testing.assert_allclose(K.digest(o.fake_B)[2:], kb["fake_B0.digest"][2:], atol=5e-6)
+
+
+def test_twostage_config3_oracle_port_reproduces_reference(replay_twostage):
+    kb, rp = np.load(K.path_of("twostage_config3")), replay_twostage
+    _check_seeded(kb, rp)
+    o = ON.TwoStageStep(rp["G1"], rp["G2"], rp["F2"], rp["D1"], rp["D2"], TWOSTAGE_CFG, dtype=torch.float32)
+    got = o.step(*rp["reals"][0], torch.from_numpy(kb["noise1_0"]), torch.from_numpy(kb["noise2_0"]))
+    np.testing.assert_allclose(np.asarray(got, dtype=np.float64), kb["loss0"], rtol=2e-5)
+    np.testing.assert_allclose(K.digest(o.fake_A)[2:], kb["fake_A0.digest"][2:], atol=5e-6)
+    np.testing.assert_allclose(K.digest(o.fake_B_from_fake_A)[2:], kb["fake_B_from_fake_A0.digest"][2:], atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["cgan_config2", "twostage_config3"])
+def test_live_reference_regenerates_config2_3_fixtures(name):
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    kb = np.load(K.path_of(name))
+    blob = K.RUNS[name]()
+    assert sorted(blob.keys()) == sorted(kb.files)
+    for k in kb.files:
+        if k.startswith(("init.", "real", "noise", "meta.")):
+            np.testing.assert_array_equal(blob[k], kb[k], err_msg=k)
+        elif k.startswith("loss"):
+            np.testing.assert_allclose(blob[k], kb[k], rtol=1e-5 if k == "loss0" else 5e-3, err_msg=k)
+        else:
+            np.testing.assert_allclose(blob[k][2:], kb[k][2:], atol=1e-5 if "0.digest" in k else 5e-3, err_msg=k)
+
+
+def _model_opt(**kw):
+    d = dict(isTrain=True, gpu_ids=[0], checkpoints_dir="/tmp/sgk_ckpt", name="t", pretrained_model_dir="", batchSize=1,
+             norm="instance", add_gaussian_noise=False, gaussian_sigma=0.1, continue_train=False, which_epoch="latest",
+             pool_size=0, lr=2e-4, beta1=0.5, no_logD_trick=False, niter_decay=100, weights=None, no_cgan=False,
+             dataset_mode="single", which_direction="AtoB", lambda_A=10.0, transform_1to2="none", which_channel="rg_b",
+             fineSize=512, input_nc=2, output_nc=1)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def _img_err(t, dig):
+    return float(np.abs(K.digest(t)[2:] - dig[2:]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,loss_tol,img_tol", [("fp32", 2e-4, 5e-5), ("tf32", 3e-3, 1e-2)])
+def test_cuda_cgan_config2_reproduces_reference(replay_cgan, precision, loss_tol, img_tol):
+    import supervised_gan_b200 as S
+    from supervised_gan_b200.cgan_model import CGANModel
+    kb, rp = np.load(K.path_of("cgan_config2")), replay_cgan
+    S.set_precision(precision)
+    try:
+        m = CGANModel()
+        m.initialize(_model_opt(noise_nc=8, noiseSize=4, ngf=64, ndf=64, which_model_netG="unet_256", which_model_netD="n_layers",
+                                no_dropout=True, n_layers_G=5, use_residual=False, upsample_mode="convt", n_layers_CRN_block=1,
+                                no_share_label_block_weights=False, n_layers_G_skip=-1, no_lsgan=True, scale_factor=[1, 1],
+                                n_layers_D=[3, 4], lambda_D=[0.5, 0.5], weights=[2.0, 4.0], n_update_D=1, n_update_G=1))
+        m.netG.load_state_dict(rp["sdG"])
+        for d, sd in zip(m.netD, rp["sdDs"]):
+            d.load_state_dict(sd)
+        S.ops.bump_weights_epoch()
+        for t in range(K.STEPS):
+            m.input_A, m.input_B = rp["reals"][t][0].cuda(), rp["reals"][t][1].cuda()
+            m.optimize_parameters()
+            e = m.get_current_errors()
+            got = [e["G_GAN"], e["G_L1"], e["D_real"], e["D_fake"]]
+            err = _img_err(m.fake_B, kb["fake_B%d.digest" % t])
+            _log("known_answer_cgan_config2", {"precision": precision, "step": t, "got": got, "ref": kb["loss%d" % t].tolist(), "fake_B": err})
+            np.testing.assert_allclose(got, kb["loss%d" % t], rtol=loss_tol if t == 0 else max(loss_tol, 1e-2))
+            if t == 0:
+                assert err <= img_tol
+    finally:
+        S.set_precision("fp32")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,loss_tol,tolA,tolB", [("fp32", 5e-4, 5e-5, 1e-4), ("tf32", 5e-3, 3e-3, 2e-2)])
+def test_cuda_twostage_config3_reproduces_reference(replay_twostage, precision, loss_tol, tolA, tolB):
+    import supervised_gan_b200 as S
+    from supervised_gan_b200.twostage_cycle_model import TwoStageCycleModel
+    kb, rp = np.load(K.path_of("twostage_config3")), replay_twostage
+    S.set_precision(precision)
+    try:
+        m = TwoStageCycleModel()
+        m.initialize(_model_opt(
+            noise_nc1=8, noiseSize1=4, noise_nc2=8, noiseSize2=8, ngf1=32, ngf2=64, nff2=32, ndf1=32, ndf2=64,
+            which_model_netG1="fcgan", which_model_netG2="crn", which_model_netF2="unet_128", which_model_netD1="n_layers",
+            which_model_netD2="n_layers", which_model_netD="n_layers", n_layers_G1=5, n_layers_G2=5, n_layers_F2=5,
+            no_dropout1=True, no_dropout2=True, use_residual2=False, upsample_mode1="convt", upsample_mode2="bilinear",
+            n_layers_CRN_block1=1, n_layers_CRN_block2=2, no_share_label_block_weights1=False,
+            no_share_label_block_weights2=False, transform_1to2="bilinear_2", scale_factor1=[1, 2], lambda_D1=[0.5, 0.4],
+            n_layers_D1=[3, 3], scale_factor2=[1, 1, 2, 2], lambda_D2=[0.3, 0.3, 0.2, 0.2], n_layers_D2=[3, 4, 3, 4],
+            no_lsgan1=True, no_lsgan2=True, use_multi_class_GAN=False, use_fixed_noise1=False, sequential_train=False,
+            lr1=2e-4, lr2=2e-4, n_update_D1=1, n_update_D2=1, n_update_G=1, detach_G1_from_G2_x=False,
+            detach_G1_from_G2_y=False, GAN_losses_D2=["real_fake"], GAN_losses_G2=["real_fake"], lambda_B=10.0,
+            lambda_A_cycle=5.0, lambda_fake_cycle=1.0))
+        for lab, net in (("G1", m.netG1), ("G2", m.netG2), ("F2", m.netF2)):
+            net.load_state_dict(rp[lab])
+        for d, sd in zip(m.netD1, rp["D1"]):
+            d.load_state_dict(sd)
+        for d, sd in zip(m.netD2, rp["D2"]):
+            d.load_state_dict(sd)
+        S.ops.bump_weights_epoch()
+        for t in range(K.STEPS):
+            m.input_A, m.input_B = rp["reals"][t][0].cuda(), rp["reals"][t][1].cuda()
+            n1, n2 = torch.from_numpy(kb["noise1_%d" % t]).cuda(), torch.from_numpy(kb["noise2_%d" % t]).cuda()
+            m._draw_noises = lambda: (n1, n2)
+            m.optimize_parameters()
+            e = m.get_current_errors()
+            got = [float(m.loss_G), e["G1_GAN"], e["G2_GAN"], e["G2_L1"], e["F2_CE"], e["G2_real_cycle"], e["G2_fake_cycle"],
+                   e["D1_real"], e["D1_fake"], e["D2_real"], e["D2_fake"]]
+            errA = _img_err(m.fake_A, kb["fake_A%d.digest" % t])
+            errB = _img_err(m.fake_B_from_fake_A, kb["fake_B_from_fake_A%d.digest" % t])
+            _log("known_answer_twostage_config3", {"precision": precision, "step": t, "got": got, "ref": kb["loss%d" % t].tolist(),
+                                                   "fake_A": errA, "fake_B": errB})
+            np.testing.assert_allclose(got, kb["loss%d" % t], rtol=loss_tol if t == 0 else max(loss_tol, 2e-2))
+            if t == 0:
+                assert errA <= tolA and errB <= tolB
+    finally:
+        S.set_precision("fp32")
