@@ -125,7 +125,9 @@ def test_cuda_step_reproduces_known_answer(ka, replay, precision, loss_tol, img_
         for t in range(K.STEPS):
             m.input = replay["reals"][t].cuda()
             m.optimize_parameters()
-            got = [float(m.loss_G), float(m.loss_D_real), float(m.loss_D_fake)]
+            got = [float(m.loss_G.detach()), float(m.loss_D_real.detach()), float(m.loss_D_fake.detach())]
+            _log("known_answer_fcgan_config1", {"precision": precision, "step": t, "got": got, "ref": ka["loss%d" % t].tolist(),
+                                                "fake": _img_err(m.fake, ka["fake%d.digest" % t])})
             # step 1 starts from weights that moved by ~lr * sign(g): sign flips of near-zero gradients are legitimate
             np.testing.assert_allclose(got, ka["loss%d" % t], rtol=loss_tol if t == 0 else max(loss_tol, 5e-3))
             if t == 0:
